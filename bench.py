@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- GRAPE iterations/s on BASELINE.json's config (C2 by default) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C1] [--batch B] [--impl ours|reference]
+
+A "step" is one GRAPE optimiser iteration of the whole batch: one fwd+bwd (value_and_grad over all
+T time steps for all B instances) plus the TF1-form Adam update.  ``value`` counts
+instance-iterations/s (B * N iterations of ONE problem instance per step), which is the unit the
+reference arm can be timed in too (it has no batch dimension: one instance per Grape() call).
+
+Keys follow the driver contract: value = device-resident throughput (CUDA events, max over ranks);
+e2e = the same step through the host-buffer C-ABI call (pinned H2D of the weights, D2H of gradient
+and losses, Adam on the host); roofline = the dominant kernel (k_expm) against the FP64 peak;
+cpu_baseline = the CPU oracle in reference-cost mode on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "quantum-optimal-control_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "GRAPE iterations/sec (fwd+bwd over T steps + Adam), summed over the batch of instances"
+UNIT = "instance-iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default: the config's)")
+    ap.add_argument("--steps-T", type=int, default=None, help="override the number of time steps (debug only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def make_problem(name, T=None):
+    import workloads as W
+    fn, meta = W.WORKLOADS[name]
+    pb = fn() if T is None else fn(T=T)
+    if T is not None:
+        full = fn()
+        pb['total_time'] = full['total_time'] * T / full['steps']      # same dt
+    return pb, dict(meta)
+
+
+def flops_alg(n, T, m, K, p, s):
+    """algorithmic real flops per instance per iteration."""
+    return 8.0 * n ** 3 * T * (p + s) + 8.0 * n ** 2 * m * T * (K + 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:  # noqa: BLE001
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle in reference-cost mode (fp32 real-embedded graph,
+# TWO fwd+bwd per optimiser iteration, backward re-computes every propagator) -- the only place
+# bench.py executes oracle/.
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(pb, steps, warmup, budget_s=None, T_sample=None):
+    import torch
+    import workloads as W
+    from oracle import grape_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    K, T = len(pb['Hops']), pb['steps']
+    Ts = T if T_sample is None else T_sample
+    pbs = dict(pb)
+    if Ts != T:
+        pbs['steps'] = Ts
+        pbs['total_time'] = pb['total_time'] * Ts / T
+    args, kw = W.grape_kwargs(pbs)
+    H0, Hops, Hn, U, tt, st, scl = args
+    guess = W.random_guess(K, Ts, pb['maxA'], 0)
+    setup = O.make_setup(H0, Hops, U, tt, st, scl, initial_guess=guess, **kw)
+    base = np.asarray(setup.ops_weight_base, dtype=np.float32)
+    adam = O.TF1Adam(base.shape, dtype=np.float32)
+
+    def one_iteration(base):
+        O.graph_value_and_grad(setup, base, torch.float32)            # run_session.py:53-54
+        out = O.graph_value_and_grad(setup, base, torch.float32)      # :69 runs the graph again
+        return adam.step(base, out.grad, 0.01)
+
+    for _ in range(warmup):
+        base = one_iteration(base)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        base = one_iteration(base)
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_start > budget_s and i >= 1:
+            break
+    per_iter = float(np.mean(times)) * (T / Ts)                        # cost is linear in T
+    return 1.0 / per_iter, cores, len(times), Ts, per_iter
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pb, meta = make_problem(args.workload, args.steps_T)
+    n, K, T, m = len(pb['H0']), len(pb['Hops']), pb['steps'], len(pb['states_concerned_list'])
+    rate, cores, done, Ts, per_iter = cpu_reference_rate(pb, args.steps, min(args.warmup, 1), budget_s=240.0)
+    sample = "1 instance x %d reference-style Adam iterations (2 fwd+bwd each, fp32 real-embedded 2n x 2n, T=%d)" % (done, Ts)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": min(args.warmup, 1), "ms_per_step": per_iter * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: n=%d K=%d T=%d m=%d, one instance per step (the reference has no batch dim)" % (
+            args.workload, n, K, T, m), "note": "CPU oracle port in reference-cost mode; TF1/py2 reference cannot run here"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import workloads as W
+    from quantum_optimal_control.core.problem import SystemParameters
+    from quantum_optimal_control.core.engine import GrapeEngine
+    from quantum_optimal_control.core.optimizer import TF1AdamState, TF1AdamHost as HostAdam
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    pb, meta = make_problem(args.workload, args.steps_T)
+    B = args.batch or meta['B']
+    n, K, T, m = len(pb['H0']), len(pb['Hops']), pb['steps'], len(pb['states_concerned_list'])
+    guess = W.random_guess(K, T, pb['maxA'], 1000 * rank, B=B)           # each rank: its own B seeds (weak scaling)
+    pargs, kw = W.grape_kwargs(pb)
+    H0, Hops, Hn, U, tt, steps, scl = pargs
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        sp = SystemParameters(H0, Hops, Hn, U, np.identity(n), tt, steps, scl, None, kw['maxA'], None, guess, False,
+                              kw.get('unitary_error', 1e-4), False, False, kw.get('reg_coeffs'), False, None,
+                              kw.get('Taylor_terms'), True, True, False, False, False)
+    eng = GrapeEngine.from_sys_para(sp, device=dev)
+    p, s = sp.exp_terms, sp.scaling
+    base0 = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop: value --------------------------------------------------------
+    base = base0.clone()
+    adam = TF1AdamState(base)
+    out = None
+    lr = 0.01
+
+    def step():
+        nonlocal out
+        out = eng.value_and_grad(base, out=out)
+        adam.step(base, out['grad'], lr)
+
+    for _ in range(args.warmup):
+        step()
+    eng.set_profiling(True)
+    ktimes = {k: 0.0 for k in eng.KERNELS}
+    launches0 = eng.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+            for k, v in eng.kernel_times_ms().items():      # syncs on the step's last kernel event only
+                ktimes[k] += v
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    eng.set_profiling(False)
+    final_loss = float(out['loss'].min().item())
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    ms_per_step = ms_max / args.steps
+    value = B * world * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    hbase = np.ascontiguousarray(sp.ops_weight_base, dtype=np.float64)
+    hadam = HostAdam(hbase.shape)
+    for _ in range(max(1, min(args.warmup, 2))):
+        o = eng.value_and_grad_host(hbase)
+        hbase = hadam.step(hbase, o['grad'], lr)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        o = eng.value_and_grad_host(hbase)
+        hbase = hadam.step(hbase, o['grad'], lr)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * e2e_steps / float(t_e.item())
+    h2d = hbase.nbytes
+    d2h = hbase.nbytes + 4 * B * 8
+
+    # ---- roofline of the dominant kernel (k_expm) ----------------------------------------------
+    peak, peak_src = None, None
+    if rank == 0:
+        a = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
+        bb = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
+        for _ in range(2):
+            a @ bb
+        best = 1e9
+        for _ in range(5):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(); a @ bb; s1.record(); torch.cuda.synchronize()
+            best = min(best, s0.elapsed_time(s1))
+        peak = 2 * 4096 ** 3 / best / 1e9
+        peak_src = "cuBLAS DGEMM 4096^3 via torch.matmul, best of 5, measured in this run (MEASURED_PEAKS.json has no fp64 entry)"
+        del a, bb
+    expm_ms = ktimes['expm'] / args.steps
+    expm_flops = 8.0 * n ** 3 * (p - 1 + s) * T * B                    # (p-1) Taylor products + s squarings per (b,t)
+    achieved = expm_flops / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else None
+    step_flops = flops_alg(n, T, m, K, p, s) * B
+    roof = {"kernel": "k_expm", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+            "peak_source": peak_src, "pipe": "fp64 (tcgen05 has no f64 kind; bound is the FP64 FMA/DMMA pipe)",
+            "alg_flops_per_launch": expm_flops, "avg_launch_ms": expm_ms,
+            "kernel_ms_per_step": {k: v / args.steps for k, v in ktimes.items()},
+            "whole_step_alg_tflops": step_flops / (ms_per_step * 1e-3) / 1e12}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            rate, cores, done, Ts, per_iter = cpu_reference_rate(pb, 50, 1, budget_s=args.cpu_seconds)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "1 instance x %d reference-style Adam iterations (2 fwd+bwd each, fp32 real-embedded, T=%d); "
+                             "%.3f s per iteration" % (done, Ts, per_iter)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: n=%d K=%d T=%d m=%d B=%d per GPU, (p,s)=(%d,%d), fp64" % (
+                args.workload, n, K, T, m, B, p, s), "batch_iterations_per_s": args.steps / (ms_max * 1e-3),
+                "l2": "inputs exceed L2: %.2f GB of propagators are rewritten and re-read every step" % (
+                    B * T * n * n * 16 / 1e9), "final_loss_min": final_loss},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,361 @@
+// C-ABI front end of libqoc_b200.so (declared in include/qoc_b200.h).
+#include "qoc_internal.cuh"
+#include <cstring>
+#include <cstdio>
+#include <vector>
+#include <new>
+
+#define QOC_CHECK_H(h) do { if (!(h)) return QOC_EINVAL; } while (0)
+#define CUDA_TRY(h, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e); return QOC_ECUDA; } } while (0)
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static int pick_np(int n) {
+  if (n <= 8) return 8;
+  if (n <= 16) return 16;
+  if (n <= 32) return 32;
+  if (n <= 48) return 48;
+  if (n <= 64) return 64;
+  return -1;
+}
+
+struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, total; };
+
+static WsLayout ws_layout(const qoc_dims_t& d) {
+  WsLayout L;
+  const size_t nn = (size_t)d.n * d.n, mn = (size_t)d.m * d.n;
+  const size_t pel = d.dtype == QOC_F64 ? sizeof(cplx) : sizeof(float2);
+  size_t off = 0;
+  L.P = off; off += align_up((size_t)d.B * d.T * nn * pel);
+  L.psi = off; off += align_up((size_t)d.B * (d.T + 1) * mn * sizeof(cplx));
+  L.lam = off; off += align_up((size_t)d.B * (d.T + 1) * mn * sizeof(cplx));
+  L.gctrl = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
+  L.ot = off; off += align_up((size_t)d.B * (d.T + 1) * sizeof(cplx));
+  L.scal = off; off += align_up((size_t)d.B * 8 * sizeof(double));
+  L.Ufin = off; off += align_up((size_t)d.B * nn * sizeof(cplx));
+  L.st_base = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
+  L.st_grad = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
+  L.st_out = off; off += align_up((size_t)d.B * 4 * sizeof(double));
+  L.total = off;
+  return L;
+}
+
+extern "C" {
+
+int qoc_abi_version(void) { return QOC_ABI_VERSION; }
+
+int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
+  if (!out || !dims) return QOC_EINVAL;
+  *out = nullptr;
+  const qoc_dims_t& d = *dims;
+  if (d.n < 1 || d.K < 0 || d.K > 32 || d.T < 1 || d.m < 1 || d.B < 1 || d.exp_terms < 1 || d.scaling < 0 ||
+      d.scaling > 60)
+    return QOC_EINVAL;
+  if (d.dtype != QOC_F64 && d.dtype != QOC_TF32X3) return QOC_EINVAL;
+  qoc_handle_s* h = new (std::nothrow) qoc_handle_s();
+  if (!h) return QOC_ENOMEM;
+  h->d = d;
+  h->NP = pick_np(d.n);
+  h->problem_set = h->ws_set = false;
+  h->A = h->U0 = h->phi = h->V = h->coo_v = nullptr;
+  h->cidx = h->coo_off = h->coo_r = h->coo_c = nullptr;
+  h->maxA = h->env = h->fw = nullptr;
+  h->has_cidx = 0; h->nnz = 0; h->dt = 0.0;
+  std::memset(&h->reg, 0, sizeof(h->reg));
+  h->ws = nullptr; h->ws_bytes = 0;
+  h->launches = 0;
+  h->sm_count = 0;
+  h->profiling = false; h->ev_recorded = 0;
+  for (int i = 0; i <= QOC_NUM_KERNELS; ++i) h->ev[i] = nullptr;
+  *out = h;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) {
+    h->err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+    return QOC_ECUDA;
+  }
+  if (d.dtype == QOC_F64 && h->NP < 0) {
+    h->err = "QOC_F64 supports n <= 64";
+    return QOC_EINVAL;
+  }
+  if (d.dtype == QOC_TF32X3) {
+    h->err = "QOC_TF32X3 is not available in this build";
+    return QOC_EINVAL;
+  }
+  return QOC_OK;
+}
+
+int qoc_destroy(qoc_handle_t h) {
+  QOC_CHECK_H(h);
+  cudaFree(h->A); cudaFree(h->U0); cudaFree(h->phi); cudaFree(h->V); cudaFree(h->coo_v);
+  cudaFree(h->cidx); cudaFree(h->coo_off); cudaFree(h->coo_r); cudaFree(h->coo_c);
+  cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw);
+  for (int i = 0; i <= QOC_NUM_KERNELS; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return QOC_OK;
+}
+
+const char* qoc_last_error(qoc_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int qoc_workspace_bytes(qoc_handle_t h, size_t* bytes) {
+  QOC_CHECK_H(h);
+  if (!bytes) return QOC_EINVAL;
+  *bytes = ws_layout(h->d).total;
+  return QOC_OK;
+}
+
+int qoc_set_workspace(qoc_handle_t h, void* dev_ptr, size_t bytes) {
+  QOC_CHECK_H(h);
+  const WsLayout L = ws_layout(h->d);
+  if (!dev_ptr || ((uintptr_t)dev_ptr & 255)) { h->err = "workspace must be 256-byte aligned"; return QOC_EINVAL; }
+  if (bytes < L.total) { h->err = "workspace too small"; return QOC_ENOMEM; }
+  char* w = (char*)dev_ptr;
+  h->ws = w; h->ws_bytes = bytes;
+  h->P = w + L.P;
+  h->psi = (cplx*)(w + L.psi); h->lam = (cplx*)(w + L.lam);
+  h->gctrl = (double*)(w + L.gctrl); h->ot = (cplx*)(w + L.ot); h->scal = (double*)(w + L.scal);
+  h->Ufin = (cplx*)(w + L.Ufin);
+  h->st_base = (double*)(w + L.st_base); h->st_grad = (double*)(w + L.st_grad); h->st_out = (double*)(w + L.st_out);
+  h->ws_set = true;
+  return QOC_OK;
+}
+
+}  // extern "C"
+
+template <typename T>
+static cudaError_t upload(T** dst, const void* src, size_t count, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  if (count == 0) count = 1;
+  e = cudaMalloc((void**)dst, count * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (src) e = cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st);
+  else e = cudaMemsetAsync(*dst, 0, count * sizeof(T), st);
+  return e;
+}
+
+extern "C" {
+
+int qoc_set_problem(qoc_handle_t h, const double* A_host, const double* U0_host, const double* phi_host,
+                    const double* V_host, const int32_t* concerned_idx, const double* maxA_host, double dt,
+                    void* stream) {
+  QOC_CHECK_H(h);
+  if (!A_host || !U0_host || !phi_host || !V_host || (h->d.K > 0 && !maxA_host)) { h->err = "null problem array"; return QOC_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const qoc_dims_t& d = h->d;
+  const size_t nn = (size_t)d.n * d.n, mn = (size_t)d.m * d.n;
+  if (concerned_idx)
+    for (int j = 0; j < d.m; ++j)
+      if (concerned_idx[j] < 0 || concerned_idx[j] >= d.n) { h->err = "concerned_idx out of range"; return QOC_EINVAL; }
+  // sparse (COO) form of the control operators A_1..A_K for the gradient kernel
+  std::vector<int> off(d.K + 1, 0), rr, cc;
+  std::vector<double> vv;
+  for (int k = 0; k < d.K; ++k) {
+    const double* Ak = A_host + (size_t)(k + 1) * nn * 2;
+    for (int r = 0; r < d.n; ++r)
+      for (int c = 0; c < d.n; ++c) {
+        const double re = Ak[((size_t)r * d.n + c) * 2], im = Ak[((size_t)r * d.n + c) * 2 + 1];
+        if (re != 0.0 || im != 0.0) { rr.push_back(r); cc.push_back(c); vv.push_back(re); vv.push_back(im); }
+      }
+    off[k + 1] = (int)rr.size();
+  }
+  h->nnz = (int)rr.size();
+  CUDA_TRY(h, upload(&h->A, A_host, (size_t)(d.K + 1) * nn, st));
+  CUDA_TRY(h, upload(&h->U0, U0_host, nn, st));
+  CUDA_TRY(h, upload(&h->phi, phi_host, mn, st));
+  CUDA_TRY(h, upload(&h->V, V_host, mn, st));
+  CUDA_TRY(h, upload(&h->cidx, concerned_idx, (size_t)d.m, st));
+  CUDA_TRY(h, upload(&h->maxA, maxA_host, (size_t)d.K, st));
+  CUDA_TRY(h, upload(&h->coo_off, off.data(), off.size(), st));
+  CUDA_TRY(h, upload(&h->coo_r, rr.data(), rr.size(), st));
+  CUDA_TRY(h, upload(&h->coo_c, cc.data(), cc.size(), st));
+  CUDA_TRY(h, upload(&h->coo_v, vv.data(), vv.size() / 2, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));       // host vectors above go out of scope
+  h->has_cidx = concerned_idx ? 1 : 0;
+  h->dt = dt;
+  h->problem_set = true;
+  return QOC_OK;
+}
+
+int qoc_set_regularizers(qoc_handle_t h, const qoc_reg_t* reg, const double* envelope_host,
+                         const double* forbid_weight_host, void* stream) {
+  QOC_CHECK_H(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!reg) { std::memset(&h->reg, 0, sizeof(h->reg)); return QOC_OK; }
+  if (reg->has_envelope && !envelope_host) { h->err = "envelope array required"; return QOC_EINVAL; }
+  if (reg->has_forbidden && !forbid_weight_host) { h->err = "forbid_weight array required"; return QOC_EINVAL; }
+  if (reg->has_d2wdt2 && !reg->has_dwdt) {
+    // the reference raises NameError here (regularization_functions.py:30 vs :41); the Python layer
+    // reproduces that, the C layer just refuses.
+    h->err = "'d2wdt2' requires 'dwdt'"; return QOC_EINVAL;
+  }
+  h->reg = *reg;
+  if (reg->has_envelope) CUDA_TRY(h, upload(&h->env, envelope_host, (size_t)h->d.K * h->d.T, st));
+  if (reg->has_forbidden) CUDA_TRY(h, upload(&h->fw, forbid_weight_host, (size_t)h->d.n, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QOC_OK;
+}
+
+static int fill_params(qoc_handle_t h, QocParams& p, const double* base) {
+  if (!h->ws_set) { h->err = "qoc_set_workspace not called"; return QOC_ESTATE; }
+  if (!h->problem_set) { h->err = "qoc_set_problem not called"; return QOC_ESTATE; }
+  if (!base) { h->err = "base is null"; return QOC_EINVAL; }
+  const qoc_dims_t& d = h->d;
+  std::memset(&p, 0, sizeof(p));
+  p.n = d.n; p.K = d.K; p.T = d.T; p.m = d.m; p.B = d.B; p.p = d.exp_terms; p.s = d.scaling;
+  p.has_cidx = h->has_cidx;
+  p.dt = h->dt; p.inv2s = 1.0 / (double)(1ull << d.scaling);
+  p.A = h->A; p.U0 = h->U0; p.phi = h->phi; p.V = h->V; p.cidx = h->cidx; p.maxA = h->maxA;
+  p.env = h->env; p.fw = h->fw;
+  p.coo_off = h->coo_off; p.coo_r = h->coo_r; p.coo_c = h->coo_c; p.coo_v = h->coo_v;
+  p.reg = h->reg;
+  p.base = base;
+  p.P = h->P; p.psi = h->psi; p.lam = h->lam; p.gctrl = h->gctrl; p.ot = h->ot; p.scal = h->scal; p.Ufin = h->Ufin;
+  return QOC_OK;
+}
+
+// per-kernel CUDA-event timing (qoc_set_profiling): event i is recorded before kernel i, event
+// QOC_NUM_KERNELS after the last one
+static int prof_mark(qoc_handle_t h, int i, cudaStream_t st) {
+  if (!h->profiling) return QOC_OK;
+  CUDA_TRY(h, cudaEventRecord(h->ev[i], st));
+  if (i + 1 > h->ev_recorded) h->ev_recorded = i + 1;
+  return QOC_OK;
+}
+
+static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
+  int rc;
+  h->ev_recorded = 0;
+  if ((rc = prof_mark(h, 0, st))) return rc;
+  CUDA_TRY(h, qoc_launch_expm_f64(p, h->NP, h->sm_count, st, &h->launches));
+  if ((rc = prof_mark(h, 1, st))) return rc;
+  CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, st, &h->launches));
+  if ((rc = prof_mark(h, 2, st))) return rc;
+  CUDA_TRY(h, qoc_launch_fwd_reduce(p, st, &h->launches));
+  if ((rc = prof_mark(h, 3, st))) return rc;
+  return QOC_OK;
+}
+
+int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev, double* reg_loss_dev,
+                       double* grad_dev, double* unitary_scale_dev, double* grad_squared_dev, void* stream) {
+  QOC_CHECK_H(h);
+  QocParams p;
+  int rc = fill_params(h, p, base_dev);
+  if (rc) return rc;
+  if (!grad_dev) { h->err = "grad is null"; return QOC_EINVAL; }
+  p.loss = loss_dev; p.reg_loss = reg_loss_dev; p.grad = grad_dev;
+  p.unitary_scale = unitary_scale_dev; p.grad_squared = grad_squared_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = run_forward(h, p, st);
+  if (rc) return rc;
+  CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
+  if ((rc = prof_mark(h, 4, st))) return rc;
+  CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, st, &h->launches));
+  if ((rc = prof_mark(h, 5, st))) return rc;
+  CUDA_TRY(h, qoc_launch_finalize(p, st, &h->launches));
+  if ((rc = prof_mark(h, 6, st))) return rc;
+  return QOC_OK;
+}
+
+int qoc_evolve(qoc_handle_t h, const double* base_dev, double* U_final_dev, double* inter_vecs_dev,
+               double* loss_dev, double* unitary_scale_dev, void* stream) {
+  QOC_CHECK_H(h);
+  QocParams p;
+  int rc = fill_params(h, p, base_dev);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = run_forward(h, p, st);
+  if (rc) return rc;
+  const qoc_dims_t& d = h->d;
+  if (U_final_dev)
+    CUDA_TRY(h, cudaMemcpyAsync(U_final_dev, h->Ufin, (size_t)d.B * d.n * d.n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  if (inter_vecs_dev)
+    CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_dev, h->psi, (size_t)d.B * (d.T + 1) * d.m * d.n * sizeof(cplx),
+                                cudaMemcpyDeviceToDevice, st));
+  if (loss_dev)
+    CUDA_TRY(h, cudaMemcpy2DAsync(loss_dev, sizeof(double), h->scal + 2, 8 * sizeof(double), sizeof(double), d.B,
+                                  cudaMemcpyDeviceToDevice, st));
+  if (unitary_scale_dev)
+    CUDA_TRY(h, cudaMemcpy2DAsync(unitary_scale_dev, sizeof(double), h->scal + 5, 8 * sizeof(double), sizeof(double),
+                                  d.B, cudaMemcpyDeviceToDevice, st));
+  return QOC_OK;
+}
+
+int qoc_value_and_grad_host(qoc_handle_t h, const double* base_host, double* loss_host, double* reg_loss_host,
+                            double* grad_host, double* unitary_scale_host, double* grad_squared_host,
+                            void* stream) {
+  QOC_CHECK_H(h);
+  if (!h->ws_set) { h->err = "qoc_set_workspace not called"; return QOC_ESTATE; }
+  if (!base_host || !grad_host) { h->err = "null host buffer"; return QOC_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const qoc_dims_t& d = h->d;
+  const size_t nb = (size_t)d.B * d.K * d.T * sizeof(double), sb = (size_t)d.B * sizeof(double);
+  CUDA_TRY(h, cudaMemcpyAsync(h->st_base, base_host, nb, cudaMemcpyHostToDevice, st));
+  double* o = h->st_out;
+  int rc = qoc_value_and_grad(h, h->st_base, o, o + d.B, h->st_grad, o + 2 * d.B, o + 3 * d.B, stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(grad_host, h->st_grad, nb, cudaMemcpyDeviceToHost, st));
+  if (loss_host) CUDA_TRY(h, cudaMemcpyAsync(loss_host, o, sb, cudaMemcpyDeviceToHost, st));
+  if (reg_loss_host) CUDA_TRY(h, cudaMemcpyAsync(reg_loss_host, o + d.B, sb, cudaMemcpyDeviceToHost, st));
+  if (unitary_scale_host) CUDA_TRY(h, cudaMemcpyAsync(unitary_scale_host, o + 2 * d.B, sb, cudaMemcpyDeviceToHost, st));
+  if (grad_squared_host) CUDA_TRY(h, cudaMemcpyAsync(grad_squared_host, o + 3 * d.B, sb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QOC_OK;
+}
+
+int qoc_evolve_host(qoc_handle_t h, const double* base_host, double* U_final_host, double* inter_vecs_host,
+                    double* loss_host, double* unitary_scale_host, void* stream) {
+  QOC_CHECK_H(h);
+  if (!h->ws_set) { h->err = "qoc_set_workspace not called"; return QOC_ESTATE; }
+  if (!base_host) { h->err = "null host buffer"; return QOC_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const qoc_dims_t& d = h->d;
+  const size_t nb = (size_t)d.B * d.K * d.T * sizeof(double);
+  CUDA_TRY(h, cudaMemcpyAsync(h->st_base, base_host, nb, cudaMemcpyHostToDevice, st));
+  double* o = h->st_out;
+  int rc = qoc_evolve(h, h->st_base, nullptr, nullptr, o, o + d.B, stream);
+  if (rc) return rc;
+  if (U_final_host)
+    CUDA_TRY(h, cudaMemcpyAsync(U_final_host, h->Ufin, (size_t)d.B * d.n * d.n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+  if (inter_vecs_host)
+    CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_host, h->psi, (size_t)d.B * (d.T + 1) * d.m * d.n * sizeof(cplx),
+                                cudaMemcpyDeviceToHost, st));
+  if (loss_host) CUDA_TRY(h, cudaMemcpyAsync(loss_host, o, d.B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (unitary_scale_host)
+    CUDA_TRY(h, cudaMemcpyAsync(unitary_scale_host, o + d.B, d.B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QOC_OK;
+}
+
+int qoc_debug_propagators(qoc_handle_t h, void** P_dev, int* elem_bytes) {
+  QOC_CHECK_H(h);
+  if (!h->ws_set) return QOC_ESTATE;
+  if (P_dev) *P_dev = h->P;
+  if (elem_bytes) *elem_bytes = h->d.dtype == QOC_F64 ? (int)sizeof(cplx) : (int)sizeof(float2);
+  return QOC_OK;
+}
+
+int64_t qoc_launch_count(qoc_handle_t h) { return h ? h->launches : -1; }
+
+int qoc_set_profiling(qoc_handle_t h, int enable) {
+  QOC_CHECK_H(h);
+  if (enable && !h->ev[0])
+    for (int i = 0; i <= QOC_NUM_KERNELS; ++i) CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+  h->profiling = enable != 0;
+  h->ev_recorded = 0;
+  return QOC_OK;
+}
+
+int qoc_kernel_times_ms(qoc_handle_t h, float* ms_out) {
+  QOC_CHECK_H(h);
+  if (!ms_out) return QOC_EINVAL;
+  for (int i = 0; i < QOC_NUM_KERNELS; ++i) ms_out[i] = 0.f;
+  if (!h->profiling || h->ev_recorded < 2) return QOC_ESTATE;
+  CUDA_TRY(h, cudaEventSynchronize(h->ev[h->ev_recorded - 1]));
+  for (int i = 0; i + 1 < h->ev_recorded; ++i) CUDA_TRY(h, cudaEventElapsedTime(&ms_out[i], h->ev[i], h->ev[i + 1]));
+  return QOC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Internal declarations shared by the kernel translation units and the C-ABI front end.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "qoc_b200.h"
+
+typedef double2 cplx;
+
+// Everything the kernels need, passed by value.
+struct QocParams {
+  int n, K, T, m, B, p, s;
+  int has_cidx;
+  double dt, inv2s;
+  // constants
+  const cplx* A;        // [K+1][n][n]
+  const cplx* U0;       // [n][n]
+  const cplx* phi;      // [m][n]
+  const cplx* V;        // [m][n]
+  const int* cidx;      // [m]
+  const double* maxA;   // [K]
+  const double* env;    // [K][T] or null
+  const double* fw;     // [n] or null   (forbidden weights, not yet /T)
+  const int* coo_off;   // [K+1]
+  const int* coo_r;     // [nnz]
+  const int* coo_c;     // [nnz]
+  const cplx* coo_v;    // [nnz]
+  qoc_reg_t reg;
+  // per-call
+  const double* base;   // [B][K][T]
+  // workspace
+  void* P;              // [B][T][n][n] complex (double2 or float2)
+  cplx* psi;            // [B][T+1][m][n]
+  cplx* lam;            // [B][T+1][m][n]
+  double* gctrl;        // [B][K][T]
+  cplx* ot;             // [B][T+1]
+  double* scal;         // [B][8]: o.re o.im loss statereg spd unitary_scale - -
+  cplx* Ufin;           // [B][n][n]
+  // outputs
+  double* loss; double* reg_loss; double* grad; double* unitary_scale; double* grad_squared;
+};
+
+struct qoc_handle_s {
+  qoc_dims_t d;
+  int NP;
+  std::string err;
+  int sm_count;
+  bool problem_set, ws_set;
+  // device constants (cudaMalloc'd by the handle; a few hundred KB)
+  cplx *A, *U0, *phi, *V, *coo_v;
+  int *cidx, *coo_off, *coo_r, *coo_c;
+  double *maxA, *env, *fw;
+  int has_cidx, nnz;
+  double dt;
+  qoc_reg_t reg;
+  // workspace carve-up
+  char* ws; size_t ws_bytes;
+  void* P; cplx *psi, *lam, *ot, *Ufin; double *gctrl, *scal;
+  double *st_base, *st_grad, *st_out;     // staging for the *_host entry points
+  int64_t launches;
+  bool profiling; int ev_recorded;
+  cudaEvent_t ev[QOC_NUM_KERNELS + 1];
+};
+
+// kernel launchers (qoc_f64.cu); return cudaError_t, bump *launches
+cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_grad(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_finalize(const QocParams& p, cudaStream_t st, int64_t* launches);

@@ -1,0 +1,289 @@
+"""ctypes binding of libqoc_b200.so (include/qoc_b200.h) + a thin torch-facing wrapper.
+
+PyTorch is plumbing here: it owns device memory (workspace, weights, results) and the stream;
+every number is produced by the hand-written sm_100a kernels behind the C ABI.  There is no CPU
+or eager fallback -- a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libqoc_b200.so")
+
+QOC_F64, QOC_TF32X3 = 0, 1
+_DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF32X3}
+
+SYMBOLS = ["qoc_abi_version", "qoc_create", "qoc_destroy", "qoc_last_error", "qoc_workspace_bytes",
+           "qoc_set_workspace", "qoc_set_problem", "qoc_set_regularizers", "qoc_value_and_grad", "qoc_evolve",
+           "qoc_value_and_grad_host", "qoc_evolve_host", "qoc_debug_propagators", "qoc_launch_count", "qoc_set_profiling",
+           "qoc_kernel_times_ms"]
+
+
+class QocDims(C.Structure):
+    _fields_ = [("n", C.c_int32), ("K", C.c_int32), ("T", C.c_int32), ("m", C.c_int32), ("B", C.c_int32),
+                ("exp_terms", C.c_int32), ("scaling", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_uint32)]
+
+
+class QocReg(C.Structure):
+    _fields_ = [("has_amplitude", C.c_int32), ("amplitude", C.c_double),
+                ("has_envelope", C.c_int32), ("envelope", C.c_double),
+                ("has_dwdt", C.c_int32), ("dwdt", C.c_double),
+                ("has_d2wdt2", C.c_int32), ("d2wdt2", C.c_double),
+                ("has_forbidden", C.c_int32),
+                ("has_speed_up", C.c_int32), ("speed_up", C.c_double)]
+
+
+class QocError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the in-tree library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise QocError("%s not found: build it with `python __graft_entry__.py` (or "
+                       "quantum-optimal-control_b200/build.py); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p
+    lib.qoc_abi_version.restype = C.c_int
+    lib.qoc_create.argtypes = [C.POINTER(vp), C.POINTER(QocDims)]
+    lib.qoc_destroy.argtypes = [vp]
+    lib.qoc_last_error.argtypes = [vp]
+    lib.qoc_last_error.restype = C.c_char_p
+    lib.qoc_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.qoc_set_workspace.argtypes = [vp, vp, C.c_size_t]
+    lib.qoc_set_problem.argtypes = [vp, dp, dp, dp, dp, ip, dp, C.c_double, vp]
+    lib.qoc_set_regularizers.argtypes = [vp, C.POINTER(QocReg), dp, dp, vp]
+    lib.qoc_value_and_grad.argtypes = [vp, dp, dp, dp, dp, dp, dp, vp]
+    lib.qoc_evolve.argtypes = [vp, dp, dp, dp, dp, dp, vp]
+    lib.qoc_value_and_grad_host.argtypes = [vp, dp, dp, dp, dp, dp, dp, vp]
+    lib.qoc_evolve_host.argtypes = [vp, dp, dp, dp, dp, dp, vp]
+    lib.qoc_debug_propagators.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int)]
+    lib.qoc_launch_count.argtypes = [vp]
+    lib.qoc_launch_count.restype = C.c_int64
+    lib.qoc_set_profiling.argtypes = [vp, C.c_int]
+    lib.qoc_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    for fn in SYMBOLS:
+        if fn not in ("qoc_last_error", "qoc_launch_count", "qoc_abi_version"):
+            getattr(lib, fn).restype = C.c_int
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def reg_struct(reg_coeffs, n, T):
+    """reg_coeffs dict (core/regularization_functions.py keys) -> (QocReg, forbid_weight[n] or None).
+    Terms are enabled by key presence, like the reference."""
+    rc = reg_coeffs or {}
+    r = QocReg()
+    for key in ('amplitude', 'envelope', 'dwdt', 'd2wdt2', 'speed_up'):
+        if key in rc:
+            setattr(r, 'has_' + key, 1)
+            setattr(r, key, float(rc[key]))
+    if 'bandpass' in rc:
+        raise ValueError('bandpass regulariser is not supported (dead code in the reference: tf.complex_abs)')
+    if 'd2wdt2' in rc and 'dwdt' not in rc:
+        raise NameError("name 'new_weights' is not defined")     # regularization_functions.py:30 vs :41
+    fw = None
+    if 'forbidden_coeff_list' in rc:
+        r.has_forbidden = 1
+        fw = np.zeros(n, dtype=np.float64)
+        for coeff, state in zip(rc['forbidden_coeff_list'], rc['states_forbidden_list']):
+            fw[int(state)] += float(coeff)
+    return r, fw
+
+
+class GrapeEngine:
+    """One problem (H_k, U_target, states, regularisers) x B independent control sets on one GPU."""
+
+    def __init__(self, n, K, T, m, B, exp_terms, scaling, dtype='f64', device=None, flags=0):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise QocError("no CUDA device visible: the GRAPE engine runs on sm_100a only (no CPU fallback)")
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device) \
+            if not isinstance(device, torch.device) else device
+        self.dims = QocDims(n, K, T, m, B, exp_terms, scaling, _DTYPES[dtype] if isinstance(dtype, str) else dtype, flags)
+        self.n, self.K, self.T, self.m, self.B = n, K, T, m, B
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.qoc_create(C.byref(self._h), C.byref(self.dims))
+            if rc:
+                msg = self.lib.qoc_last_error(self._h).decode() if self._h else "invalid dimensions"
+                if self._h:
+                    self.lib.qoc_destroy(self._h)
+                    self._h = C.c_void_p()
+                raise QocError("qoc_create failed (%d): %s" % (rc, msg))
+            nbytes = C.c_size_t()
+            self._check(self.lib.qoc_workspace_bytes(self._h, C.byref(nbytes)))
+            self.workspace_bytes = nbytes.value
+            self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+            ptr = (self._ws.data_ptr() + 255) // 256 * 256
+            self._check(self.lib.qoc_set_workspace(self._h, C.c_void_p(ptr), C.c_size_t(nbytes.value)))
+        self._pinned = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc:
+            raise QocError("libqoc_b200 error %d: %s" % (rc, self.lib.qoc_last_error(self._h).decode()))
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.qoc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def set_problem(self, A, U0, phi, V, concerned_idx, maxA, dt):
+        """A [K+1,n,n] = -i*dt*[H0, Hops...]; U0 [n,n]; phi, V [m,n]; concerned_idx [m] or None."""
+        A = np.ascontiguousarray(A, dtype=np.complex128)
+        U0 = np.ascontiguousarray(U0, dtype=np.complex128)
+        phi = np.ascontiguousarray(phi, dtype=np.complex128)
+        V = np.ascontiguousarray(V, dtype=np.complex128)
+        maxA = np.ascontiguousarray(maxA, dtype=np.float64)
+        assert A.shape == (self.K + 1, self.n, self.n) and U0.shape == (self.n, self.n)
+        assert phi.shape == (self.m, self.n) and V.shape == (self.m, self.n) and maxA.shape == (self.K,)
+        idx = None if concerned_idx is None else np.ascontiguousarray(concerned_idx, dtype=np.int32)
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.qoc_set_problem(self._h, _np_ptr(A), _np_ptr(U0), _np_ptr(phi), _np_ptr(V),
+                                                 _np_ptr(idx), _np_ptr(maxA), float(dt), self._stream()))
+
+    def set_regularizers(self, reg_coeffs, envelope=None):
+        r, fw = reg_struct(reg_coeffs, self.n, self.T)
+        env = None
+        if r.has_envelope:
+            env = np.ascontiguousarray(envelope, dtype=np.float64)
+            assert env.shape == (self.K, self.T)
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.qoc_set_regularizers(self._h, C.byref(r), _np_ptr(env), _np_ptr(fw), self._stream()))
+
+    # ------------------------------------------------------------------------------------------
+    def _base(self, base):
+        t = self.torch
+        assert base.is_cuda and base.dtype == t.float64 and base.is_contiguous()
+        assert tuple(base.shape) == (self.B, self.K, self.T), (tuple(base.shape), (self.B, self.K, self.T))
+        return base
+
+    def value_and_grad(self, base, out=None):
+        """base: cuda float64 [B,K,T] -> dict(loss, reg_loss, grad, unitary_scale, grad_squared) of
+        cuda tensors (asynchronous on the current stream).  ``out`` recycles a previous result dict."""
+        t = self.torch
+        base = self._base(base)
+        if out is None:
+            out = dict(loss=t.empty(self.B, dtype=t.float64, device=self.device),
+                       reg_loss=t.empty(self.B, dtype=t.float64, device=self.device),
+                       grad=t.empty_like(base),
+                       unitary_scale=t.empty(self.B, dtype=t.float64, device=self.device),
+                       grad_squared=t.empty(self.B, dtype=t.float64, device=self.device))
+        p = lambda x: C.c_void_p(x.data_ptr())
+        self._check(self.lib.qoc_value_and_grad(self._h, p(base), p(out['loss']), p(out['reg_loss']), p(out['grad']),
+                                                p(out['unitary_scale']), p(out['grad_squared']), self._stream()))
+        return out
+
+    def evolve(self, base, want_inter_vecs=True):
+        """Forward only -> dict(U_final [B,n,n] c128, inter_vecs [B,T+1,m,n] c128 | None, loss, unitary_scale)."""
+        t = self.torch
+        base = self._base(base)
+        U = t.empty(self.B, self.n, self.n, dtype=t.complex128, device=self.device)
+        iv = t.empty(self.B, self.T + 1, self.m, self.n, dtype=t.complex128, device=self.device) if want_inter_vecs else None
+        loss = t.empty(self.B, dtype=t.float64, device=self.device)
+        us = t.empty(self.B, dtype=t.float64, device=self.device)
+        p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+        self._check(self.lib.qoc_evolve(self._h, p(base), p(U), p(iv), p(loss), p(us), self._stream()))
+        return dict(U_final=U, inter_vecs=iv, loss=loss, unitary_scale=us)
+
+    # host-buffer entry points (the reference-facing call: run_session.get_error semantics) -----
+    def _pin(self, name, shape, dtype=np.float64):
+        t = self.torch
+        key = (name, tuple(shape), np.dtype(dtype).str)
+        if key not in self._pinned:
+            td = {np.dtype(np.float64).str: t.float64, np.dtype(np.complex128).str: t.complex128}[np.dtype(dtype).str]
+            self._pinned[key] = t.empty(tuple(shape), dtype=td).pin_memory()
+        return self._pinned[key]
+
+    def value_and_grad_host(self, base_np):
+        """NumPy in, NumPy out; H2D + kernels + D2H inside the call (pinned staging buffers)."""
+        hb = self._pin('base', (self.B, self.K, self.T))
+        hb.numpy()[...] = np.asarray(base_np, dtype=np.float64).reshape(self.B, self.K, self.T)
+        hg = self._pin('grad', (self.B, self.K, self.T))
+        ho = self._pin('out', (4, self.B))
+        p = lambda x: C.c_void_p(x.data_ptr())
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.qoc_value_and_grad_host(
+                self._h, p(hb), p(ho[0]), p(ho[1]), p(hg), p(ho[2]), p(ho[3]), self._stream()))
+        o = ho.numpy()
+        return dict(loss=o[0].copy(), reg_loss=o[1].copy(), grad=hg.numpy().copy(), unitary_scale=o[2].copy(),
+                    grad_squared=o[3].copy())
+
+    def evolve_host(self, base_np, want_inter_vecs=True):
+        hb = self._pin('base', (self.B, self.K, self.T))
+        hb.numpy()[...] = np.asarray(base_np, dtype=np.float64).reshape(self.B, self.K, self.T)
+        hU = self._pin('U', (self.B, self.n, self.n), np.complex128)
+        hiv = self._pin('iv', (self.B, self.T + 1, self.m, self.n), np.complex128) if want_inter_vecs else None
+        ho = self._pin('eout', (2, self.B))
+        p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.qoc_evolve_host(self._h, p(hb), p(hU), p(hiv), p(ho[0]), p(ho[1]), self._stream()))
+        return dict(U_final=hU.numpy().copy(), inter_vecs=None if hiv is None else hiv.numpy().copy(),
+                    loss=ho.numpy()[0].copy(), unitary_scale=ho.numpy()[1].copy())
+
+    def propagators(self):
+        """Debug view of the cached propagators P[B,T,n,n] of the last call (clone)."""
+        t = self.torch
+        ptr, eb = C.c_void_p(), C.c_int()
+        self._check(self.lib.qoc_debug_propagators(self._h, C.byref(ptr), C.byref(eb)))
+        off = ptr.value - self._ws.data_ptr()
+        nel = self.B * self.T * self.n * self.n
+        raw = self._ws[off:off + nel * eb.value]
+        dt = t.complex128 if eb.value == 16 else t.complex64
+        return raw.view(dt).reshape(self.B, self.T, self.n, self.n).clone()
+
+    KERNELS = ("expm", "chain", "fwd_reduce", "costate", "grad", "finalize")
+
+    def set_profiling(self, enable=True):
+        self._check(self.lib.qoc_set_profiling(self._h, int(bool(enable))))
+
+    def kernel_times_ms(self):
+        """Per-kernel CUDA-event durations (ms) of the last value_and_grad; synchronises."""
+        buf = (C.c_float * len(self.KERNELS))()
+        self._check(self.lib.qoc_kernel_times_ms(self._h, buf))
+        return dict(zip(self.KERNELS, [float(x) for x in buf]))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.qoc_launch_count(self._h))
+
+    @classmethod
+    def from_sys_para(cls, sp, B=None, dtype='f64', device=None):
+        """Build an engine from a ``SystemParameters`` (unitary mode)."""
+        if sp.state_transfer:
+            raise NotImplementedError("state_transfer=True is not implemented by the CUDA engine yet")
+        if sp.is_dressed and sp.reg_coeffs.get('forbid_dressed'):
+            raise NotImplementedError("forbid_dressed is not implemented by the CUDA engine yet")
+        B = sp.batch_size if B is None else B
+        eng = cls(sp.state_num, sp.ops_len, sp.steps, len(sp.states_concerned_list), B, sp.exp_terms, sp.scaling,
+                  dtype=dtype, device=device)
+        eng.set_problem(sp.A_c, sp.U0_c, sp.target_vectors_c, sp.V_c, sp.concerned_idx, sp.ops_max_amp, sp.dt)
+        eng.set_regularizers(sp.reg_coeffs, sp.one_minus_gauss)
+        return eng
