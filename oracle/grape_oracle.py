@@ -464,8 +464,8 @@ def graph_value_and_grad(setup: OracleSetup, base, dtype=torch.float64, want_gra
     iv = None
     if inter_vecs_packed is not None:
         iv = inter_vecs_packed.detach().permute(2, 0, 1).numpy().copy()         # unstack axis 2 -> m x [2n,T+1]
-    return GraphOutputs(loss=float(loss), reg_loss=float(reg_loss), grad=grad,
-                        unitary_scale=float(unitary_scale), grad_squared=grad_squared,
+    return GraphOutputs(loss=float(loss.detach()), reg_loss=float(reg_loss.detach()), grad=grad,
+                        unitary_scale=float(unitary_scale.detach()), grad_squared=grad_squared,
                         final_state=final_state.detach().numpy().copy(), inter_vecs=iv,
                         ops_weight=ops_weight.detach().numpy().copy())
 

@@ -376,17 +376,22 @@ template <>
 DEVINL cplx load_p<float2>(const float2* s, int i) { const float2 v = s[i]; return make_double2((double)v.x, (double)v.y); }
 
 template <typename PT>
-__global__ void k_costate(QocParams p, int parts, int nbuf) {
+__global__ void k_costate(QocParams p, int parts, int nbuf, int mc) {
+  // grid = (B, ceil(m/mc)): the m costate columns are independent chains, a CTA sweeps mc of them
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = p.n, m = p.m, T = p.T, nn = n * n, mn = m * n;
+  const int j0 = blockIdx.y * mc;
+  const int mloc = min(mc, m - j0);
+  const int ln = mloc * n;                                                       // local outputs
   PT* Pb = reinterpret_cast<PT*>(smem_raw);                                      // [nbuf][nn]
-  cplx* lam_s = reinterpret_cast<cplx*>(smem_raw + (size_t)nbuf * nn * sizeof(PT));   // [mn]
-  cplx* part_s = lam_s + mn;                                                     // [parts][mn]
+  cplx* lam_s = reinterpret_cast<cplx*>(smem_raw + (size_t)nbuf * nn * sizeof(PT));   // [mc*n]
+  cplx* part_s = lam_s + mc * n;                                                 // [parts][mc*n]
   const int tid = threadIdx.x, nt = blockDim.x;
   const int b = blockIdx.x;
   const PT* Pg = reinterpret_cast<const PT*>(p.P) + (size_t)b * T * nn;
-  const cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
-  cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn;
+  const cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn + (size_t)j0 * n;
+  cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn + (size_t)j0 * n;
+  const cplx* phi = p.phi + (size_t)j0 * n;
   const double* sc = p.scal + (size_t)b * 8;
   const double o_re = sc[0], o_im = sc[1], spdfac = sc[4];
   const bool forb = p.reg.has_forbidden && p.fw != nullptr;
@@ -394,7 +399,7 @@ __global__ void k_costate(QocParams p, int parts, int nbuf) {
   const double m2 = (double)m * (double)m;
   constexpr int EPV = 16 / sizeof(PT) > 0 ? 16 / sizeof(PT) : 1;                 // elements per 16 B
 
-  auto source = [&](int t, int idx) -> cplx {          // regulariser source at time t for element idx=(j,i)
+  auto source = [&](int t, int idx) -> cplx {          // regulariser source at time t for local element idx=(jl,i)
     cplx s = make_double2(0.0, 0.0);
     if (forb) {
       const cplx x = psi_b[(size_t)t * mn + idx];
@@ -404,8 +409,7 @@ __global__ void k_costate(QocParams p, int parts, int nbuf) {
     }
     if (spd) {
       const cplx o = p.ot[(size_t)b * (T + 1) + t];
-      const cplx ph = p.phi[idx];
-      const cplx q = cmul(o, ph);
+      const cplx q = cmul(o, phi[idx]);
       s.x += spdfac * q.x; s.y += spdfac * q.y;
     }
     return s;
@@ -425,9 +429,8 @@ __global__ void k_costate(QocParams p, int parts, int nbuf) {
   };
 
   // lambda(T) = -(2/m^2) * o * phi + source(T)
-  for (int idx = tid; idx < mn; idx += nt) {
-    const cplx ph = p.phi[idx];
-    cplx l = cmul(make_double2(o_re, o_im), ph);
+  for (int idx = tid; idx < ln; idx += nt) {
+    cplx l = cmul(make_double2(o_re, o_im), phi[idx]);
     l.x *= -2.0 / m2; l.y *= -2.0 / m2;
     const cplx s = source(T, idx);
     l.x += s.x; l.y += s.y;
@@ -436,14 +439,13 @@ __global__ void k_costate(QocParams p, int parts, int nbuf) {
   }
   prefetch(T - 1);
   if (nbuf > 2) prefetch(T - 2);
+  const int rchunk = (n + parts - 1) / parts;
   for (int t = T - 1; t >= 1; --t) {
     if (nbuf > 2) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();                                   // P_t landed, lam_s(t+1) complete
     const PT* Pt = Pb + (size_t)(t % nbuf) * nn;
-    // partial products: work item = (part q, output idx)
-    const int rchunk = (n + parts - 1) / parts;
-    for (int w = tid; w < parts * mn; w += nt) {
-      const int q = w / mn, idx = w - q * mn;
+    for (int w = tid; w < parts * ln; w += nt) {       // partial products: work item = (part q, output idx)
+      const int q = w / ln, idx = w - q * ln;
       const int j = idx / n, i = idx - j * n;
       const int r0 = q * rchunk, r1 = min(n, r0 + rchunk);
       cplx acc = make_double2(0.0, 0.0);
@@ -452,9 +454,9 @@ __global__ void k_costate(QocParams p, int parts, int nbuf) {
     }
     __syncthreads();
     prefetch(t - (nbuf > 2 ? 2 : 1));                  // buffer of P_{t+1} (nbuf=3) / P_t (nbuf=2) is free now
-    for (int idx = tid; idx < mn; idx += nt) {
+    for (int idx = tid; idx < ln; idx += nt) {
       cplx l = source(t, idx);
-      for (int q = 0; q < parts; ++q) { const cplx v = part_s[q * mn + idx]; l.x += v.x; l.y += v.y; }
+      for (int q = 0; q < parts; ++q) { const cplx v = part_s[q * ln + idx]; l.x += v.x; l.y += v.y; }
       lam_s[idx] = l;
       lam_b[(size_t)t * mn + idx] = l;
     }
@@ -624,26 +626,31 @@ cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* 
 
 cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches) {
   ++*launches;
-  const int mn = p.m * p.n, nn = p.n * p.n;
-  const int threads = 128;
-  int parts = threads / mn;
+  const int nn = p.n * p.n;
+  const size_t psz = p_is_f32 ? sizeof(float2) : sizeof(cplx);
+  // columns per CTA: all m when small, else chunks of <= 8 columns (more CTAs, less shared memory)
+  int mc = p.m;
+  if ((size_t)mc * p.n > 512) mc = 512 / p.n > 0 ? 512 / p.n : 1;
+  const int ln = mc * p.n;
+  const int threads = ln >= 256 ? 256 : 128;
+  int parts = threads / ln;
   if (parts < 1) parts = 1;
   if (parts > 8) parts = 8;
   if (parts > p.n) parts = p.n;
-  const size_t psz = p_is_f32 ? sizeof(float2) : sizeof(cplx);
   int nbuf = 3;
-  size_t smem = (size_t)nbuf * nn * psz + (size_t)(1 + parts) * mn * sizeof(cplx);
-  if (smem > 200 * 1024) { nbuf = 2; smem = (size_t)nbuf * nn * psz + (size_t)(1 + parts) * mn * sizeof(cplx); }
+  size_t smem = (size_t)nbuf * nn * psz + (size_t)(1 + parts) * ln * sizeof(cplx);
+  if (smem > 110 * 1024) { nbuf = 2; smem = (size_t)nbuf * nn * psz + (size_t)(1 + parts) * ln * sizeof(cplx); }
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  const dim3 grid(p.B, (p.m + mc - 1) / mc);
   cudaError_t e;
   if (p_is_f32) {
     e = cudaFuncSetAttribute(k_costate<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_costate<float2><<<p.B, threads, smem, st>>>(p, parts, nbuf);
+    k_costate<float2><<<grid, threads, smem, st>>>(p, parts, nbuf, mc);
   } else {
     e = cudaFuncSetAttribute(k_costate<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_costate<double2><<<p.B, threads, smem, st>>>(p, parts, nbuf);
+    k_costate<double2><<<grid, threads, smem, st>>>(p, parts, nbuf, mc);
   }
   return cudaGetLastError();
 }

@@ -3,7 +3,8 @@ signature and return value ``(uks, U_final)``, running on the B200 engine.
 
 Additive keywords (ours): ``batch`` (number of independent random initialisations when no
 ``initial_guess`` is given), ``dtype`` ('f64'), ``device``, ``quiet``; ``initial_guess`` may be
-[B, K, T], in which case ``uks`` is [B, K, T] and ``U_final`` is [B, n, n].
+[B, K, T], in which case ``uks`` is [B, K, T] and ``U_final`` is [B, n, n]; ``return_losses=True`` appends the
+per-instance final losses (used by ``core.population`` for multi-GPU sweeps).
 """
 import os
 import time
@@ -21,7 +22,8 @@ def Grape(H0, Hops, Hnames, U, total_time, steps, states_concerned_list, converg
           reg_coeffs=None, dressed_info=None, maxA=None, use_gpu=True, sparse_H=True, sparse_U=False,
           sparse_K=False, draw=None, initial_guess=None, show_plots=True, unitary_error=1e-4, method='Adam',
           state_transfer=False, no_scaling=False, freq_unit='GHz', file_name=None, save=True, data_path=None,
-          Taylor_terms=None, use_inter_vecs=True, batch=None, dtype='f64', device=None, quiet=False):
+          Taylor_terms=None, use_inter_vecs=True, batch=None, dtype='f64', device=None, quiet=False,
+          return_losses=False):
     grape_start_time = time.time()
     time_unit = {"GHz": "ns", "MHz": "us", "KHz": "ms", "Hz": "s"}[freq_unit]       # grape.py:25-26
 
@@ -70,6 +72,8 @@ def Grape(H0, Hops, Hnames, U, total_time, steps, states_concerned_list, converg
             storage.save_results(file_path, SS, sys_para, time.time() - grape_start_time)
             if not quiet:
                 print("data saved at: " + str(file_path))
+        if return_losses:
+            return SS.uks, SS.Uf, np.asarray(SS.l)
         return SS.uks, SS.Uf
     except KeyboardInterrupt:                                                       # grape.py:130-139
         if save:

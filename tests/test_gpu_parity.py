@@ -141,3 +141,42 @@ def test_full_size_c2_properties(built_lib):
     assert np.linalg.norm(U[0].cpu().numpy() - O.r_to_c_mat(ref.final_state, 30)) < 1e-8
     assert np.abs(out['grad'][0].cpu().numpy() - ref.grad).max() < 1e-9 * np.abs(ref.grad).max()
     eng.close()
+
+
+# ---- fixtures produced by the reference's own source (oracle/run_reference.py) ---------------------
+import os as _os
+from oracle.run_reference import golden_cases as _golden_cases
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", list(_golden_cases()))
+def test_cuda_matches_reference_goldens(name, built_lib):
+    """CUDA path vs what the reference's own graph code produced (fp64 arithmetic): one evaluation
+    (loss, reg_loss, grad, unitary_scale, U_final, inter_vecs) and a full Grape() Adam run."""
+    from quantum_optimal_control.main_grape.grape import Grape
+    g = np.load(_os.path.join(_GOLD, "ref_%s_float64.npz" % name))
+    pb, seed, conv = _golden_cases()[name]
+    args, kw = W.grape_kwargs(pb)
+    sp, eng = engine_for(args, kw, g['guess'][None])
+    assert (sp.exp_terms, sp.scaling) == (int(g['exp_terms']), int(g['scaling']))
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    out = eng.value_and_grad(base)
+    ev = eng.evolve(base)
+    n = sp.state_num
+    assert abs(out['loss'][0].item() - g['eval_loss']) < 1e-10
+    assert abs(out['reg_loss'][0].item() - g['eval_reg_loss']) < 1e-10 * max(1, abs(g['eval_reg_loss']))
+    assert abs(out['unitary_scale'][0].item() - g['eval_unitary_scale']) < 1e-10
+    assert np.abs(out['grad'][0].cpu().numpy() - g['eval_grad']).max() < 1e-9 * max(1.0, np.abs(g['eval_grad']).max())
+    fs = g['eval_final_state']
+    assert np.linalg.norm(ev['U_final'][0].cpu().numpy() - (fs[:n, :n] + 1j * fs[n:, :n])) < 1e-9
+    ivp = g['eval_inter_vecs_packed']                                   # [2n, T+1, m]
+    iv = np.transpose(ivp[:n] + 1j * ivp[n:], (1, 2, 0))                 # [T+1, m, n]
+    assert np.abs(ev['inter_vecs'][0].cpu().numpy() - iv).max() < 1e-9
+    eng.close()
+    uks, Uf = Grape(*args, convergence=conv, initial_guess=g['guess'], save=False, show_plots=False, quiet=True, **kw)
+    assert np.abs(uks - g['uks']).max() < 1e-8
+    assert np.linalg.norm(Uf - g['U_final']) < 1e-5        # north_star bar; observed ~1e-12
+    assert np.linalg.norm(Uf - g['U_final']) < 1e-8
+    g32 = np.load(_os.path.join(_GOLD, "ref_%s_float32.npz" % name))    # the reference's real dtype
+    assert np.linalg.norm(Uf - g32['U_final']) < 2e-3
