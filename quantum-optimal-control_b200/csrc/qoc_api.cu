@@ -11,14 +11,7 @@
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-static int pick_np(int n) {
-  if (n <= 8) return 8;
-  if (n <= 16) return 16;
-  if (n <= 32) return 32;
-  if (n <= 48) return 48;
-  if (n <= 64) return 64;
-  return -1;
-}
+static int pick_np(int n) { return n <= 64 ? (n + 7) / 8 * 8 : -1; }
 
 struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, total; };
 
@@ -49,7 +42,7 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   if (!out || !dims) return QOC_EINVAL;
   *out = nullptr;
   const qoc_dims_t& d = *dims;
-  if (d.n < 1 || d.K < 0 || d.K > 32 || d.T < 1 || d.m < 1 || d.B < 1 || d.exp_terms < 1 || d.scaling < 0 ||
+  if (d.n < 1 || d.K < 0 || d.K > 31 || d.T < 1 || d.m < 1 || d.B < 1 || d.exp_terms < 1 || d.scaling < 0 ||
       d.scaling > 60)
     return QOC_EINVAL;
   if (d.dtype != QOC_F64 && d.dtype != QOC_TF32X3) return QOC_EINVAL;
@@ -58,8 +51,9 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   h->d = d;
   h->NP = pick_np(d.n);
   h->problem_set = h->ws_set = false;
-  h->A = h->U0 = h->phi = h->V = h->coo_v = nullptr;
-  h->cidx = h->coo_off = h->coo_r = h->coo_c = nullptr;
+  h->A = h->U0 = h->phi = h->V = h->coo_v = h->pat_coef = nullptr;
+  h->cidx = h->coo_off = h->coo_r = h->coo_c = h->pat_rc = nullptr;
+  h->pat_n = 0;
   h->maxA = h->env = h->fw = nullptr;
   h->has_cidx = 0; h->nnz = 0; h->dt = 0.0;
   std::memset(&h->reg, 0, sizeof(h->reg));
@@ -91,7 +85,7 @@ int qoc_destroy(qoc_handle_t h) {
   QOC_CHECK_H(h);
   cudaFree(h->A); cudaFree(h->U0); cudaFree(h->phi); cudaFree(h->V); cudaFree(h->coo_v);
   cudaFree(h->cidx); cudaFree(h->coo_off); cudaFree(h->coo_r); cudaFree(h->coo_c);
-  cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw);
+  cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw); cudaFree(h->pat_rc); cudaFree(h->pat_coef);
   for (int i = 0; i <= QOC_NUM_KERNELS; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return QOC_OK;
@@ -162,6 +156,26 @@ int qoc_set_problem(qoc_handle_t h, const double* A_host, const double* U0_host,
     off[k + 1] = (int)rr.size();
   }
   h->nnz = (int)rr.size();
+  // union sparsity pattern of A_0..A_K with per-entry coefficient vectors, for the H assembly
+  std::vector<int> prc;
+  std::vector<double> pcf;
+  for (int r = 0; r < d.n; ++r)
+    for (int c = 0; c < d.n; ++c) {
+      bool any = false;
+      for (int k = 0; k <= d.K && !any; ++k) {
+        const double* e = A_host + ((size_t)k * nn + (size_t)r * d.n + c) * 2;
+        any = e[0] != 0.0 || e[1] != 0.0;
+      }
+      if (!any) continue;
+      prc.push_back((r << 16) | c);
+      for (int k = 0; k <= d.K; ++k) {
+        const double* e = A_host + ((size_t)k * nn + (size_t)r * d.n + c) * 2;
+        pcf.push_back(e[0]); pcf.push_back(e[1]);
+      }
+    }
+  h->pat_n = (int)prc.size();
+  CUDA_TRY(h, upload(&h->pat_rc, prc.data(), prc.size(), st));
+  CUDA_TRY(h, upload(&h->pat_coef, pcf.data(), pcf.size() / 2, st));
   CUDA_TRY(h, upload(&h->A, A_host, (size_t)(d.K + 1) * nn, st));
   CUDA_TRY(h, upload(&h->U0, U0_host, nn, st));
   CUDA_TRY(h, upload(&h->phi, phi_host, mn, st));
@@ -210,6 +224,7 @@ static int fill_params(qoc_handle_t h, QocParams& p, const double* base) {
   p.A = h->A; p.U0 = h->U0; p.phi = h->phi; p.V = h->V; p.cidx = h->cidx; p.maxA = h->maxA;
   p.env = h->env; p.fw = h->fw;
   p.coo_off = h->coo_off; p.coo_r = h->coo_r; p.coo_c = h->coo_c; p.coo_v = h->coo_v;
+  p.pat_n = h->pat_n; p.pat_rc = h->pat_rc; p.pat_coef = h->pat_coef;
   p.reg = h->reg;
   p.base = base;
   p.P = h->P; p.psi = h->psi; p.lam = h->lam; p.gctrl = h->gctrl; p.ot = h->ot; p.scal = h->scal; p.Ufin = h->Ufin;

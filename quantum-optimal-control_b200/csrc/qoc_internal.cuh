@@ -25,6 +25,9 @@ struct QocParams {
   const int* coo_r;     // [nnz]
   const int* coo_c;     // [nnz]
   const cplx* coo_v;    // [nnz]
+  int pat_n;            // union sparsity pattern of A_0..A_K
+  const int* pat_rc;    // [pat_n]  (row << 16) | col
+  const cplx* pat_coef; // [pat_n][K+1]
   qoc_reg_t reg;
   // per-call
   const double* base;   // [B][K][T]
@@ -47,8 +50,9 @@ struct qoc_handle_s {
   int sm_count;
   bool problem_set, ws_set;
   // device constants (cudaMalloc'd by the handle; a few hundred KB)
-  cplx *A, *U0, *phi, *V, *coo_v;
-  int *cidx, *coo_off, *coo_r, *coo_c;
+  cplx *A, *U0, *phi, *V, *coo_v, *pat_coef;
+  int *cidx, *coo_off, *coo_r, *coo_c, *pat_rc;
+  int pat_n;
   double *maxA, *env, *fw;
   int has_cidx, nnz;
   double dt;
@@ -62,7 +66,7 @@ struct qoc_handle_s {
   cudaEvent_t ev[QOC_NUM_KERNELS + 1];
 };
 
-// kernel launchers (qoc_f64.cu); return cudaError_t, bump *launches
+// kernel launchers (qoc_mma_f64.cu, qoc_sweeps.cu); return cudaError_t, bump *launches
 cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches);

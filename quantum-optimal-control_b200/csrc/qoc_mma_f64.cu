@@ -1,0 +1,403 @@
+// FP64 tensor-pipe kernels (mma.sync.m8n8k4.f64 = DMMA) for the two GEMM-shaped stages of the
+// GRAPE hot path on sm_100a.  tcgen05 has no f64 kind, so the fp64 configuration is bounded by the
+// FP64 pipe (DFMA and DMMA both measure ~36.7-37.0 TFLOP/s on B200, profiles/r01_fp64_peaks.json);
+// DMMA is used because per FMA it needs 8x fewer issue slots and ~4x fewer shared-memory
+// wavefronts than a register-tiled DFMA loop (profiles/r01_ncu_expm_v1.md).
+//
+//   k_expm_mma : (b,t) -> P_t = (sum_{j<=p} H^j/j!)^(2^s), H = (A_0 + sum_k u_k(t) A_k)/2^s
+//                (get_matexp / matexp_op, core/tensorflow_state.py:25-46,70-75)
+//   k_chain_mma: b -> X_t = P_t X_{t-1}; psi_j(t+1) = X_t V_j; U_final; unitary_scale
+//                (init_tf_propagator / init_tf_inter_vectors, :204-242)
+//
+// Shared-memory matrix layout: NP x NP complex (double2), row-major, NP = n rounded up to 8, no
+// padding, 16-byte columns XOR-swizzled by row:  phys(r,c) = r*NP + (c ^ sw(r)),
+// sw(r) = 5*(r&1) ^ 2*((r>>1)&3).  With it every access pattern below is conflict-free per
+// quarter-warp: A fragments (rows g, 4 consecutive k), B fragments straight from the row-major
+// operand (rows k0+q, column c0+g) and the C-fragment stores.
+#include "qoc_internal.cuh"
+#include <math.h>
+
+#define DEVINL __device__ __forceinline__
+
+namespace {
+
+DEVINL double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+DEVINL void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+DEVINL int sw_mask(int r) { return ((r & 1) * 5) ^ (((r >> 1) & 3) << 1); }
+
+template <int NP>
+DEVINL int swz(int r, int c) { return r * NP + (c ^ sw_mask(r)); }
+
+// D(8x8) += A(8x4) * B(4x8), fp64.  a: A[g][q], b: B[q][g], d0/d1: D[g][2q], D[g][2q+1]
+DEVINL void dmma(double& d0, double& d1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <int NP, int RB, int CB>
+struct MT {
+  static constexpr int NBLK = NP / 8;
+  static constexpr int WR = NBLK / RB;
+  static constexpr int WC = NBLK / CB;
+  static constexpr int WARPS = WR * WC;
+  static constexpr int THREADS = 32 * WARPS;
+  static constexpr int MAT = NP * NP;
+  static_assert(NBLK % RB == 0 && NBLK % CB == 0, "tile must divide the block grid");
+};
+
+// Complex C = A * B on swizzled shared operands; the warp owns block rows [rb0, rb0+RB) and block
+// columns [cb0, cb0+CB).  cr/ci[i][j][e] = Re/Im C[8(rb0+i)+g][8(cb0+j)+2q+e].
+template <int NP, int RB, int CB>
+DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, double (&cr)[RB][CB][2],
+                     double (&ci)[RB][CB][2], int rb0, int cb0, int ksteps, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  int arow[RB], amask[RB];
+#pragma unroll
+  for (int i = 0; i < RB; ++i) {
+    const int r = 8 * (rb0 + i) + g;
+    arow[i] = r * NP;
+    amask[i] = sw_mask(r);
+#pragma unroll
+    for (int j = 0; j < CB; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+  }
+  const int bc = 8 * cb0 + g;
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k = 4 * ks + q;
+    cplx a[RB], b[CB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) a[i] = A[arow[i] + (k ^ amask[i])];
+    const int bm = sw_mask(k);
+    const cplx* Brow = B + k * NP;
+#pragma unroll
+    for (int j = 0; j < CB; ++j) b[j] = Brow[(bc + 8 * j) ^ bm];
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const double nai = -a[i].y;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], nai, b[j].y);
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
+  }
+}
+
+template <int NP, int RB, int CB>
+DEVINL void store_tile(cplx* __restrict__ M, const double (&cr)[RB][CB][2], const double (&ci)[RB][CB][2], int rb0,
+                       int cb0, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < RB; ++i) {
+    const int r = 8 * (rb0 + i) + g;
+    const int m = sw_mask(r);
+#pragma unroll
+    for (int j = 0; j < CB; ++j) {
+      const int c = 8 * (cb0 + j) + 2 * q;
+      M[r * NP + (c ^ m)] = make_double2(cr[i][j][0], ci[i][j][0]);
+      M[r * NP + ((c + 1) ^ m)] = make_double2(cr[i][j][1], ci[i][j][1]);
+    }
+  }
+}
+
+template <int WARPS>
+DEVINL void item_sync() {
+  if (WARPS == 1) __syncwarp(); else __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_expm_mma: persistent over (b,t) items.  An item is owned by WARPS warps; when WARPS == 1 a
+// CTA carries 4 independent items (one per warp), else exactly one.  Shared memory per item:
+// H, ping, pong (3 x NP^2 x 16 B) + 32 weights.
+// ---------------------------------------------------------------------------------------------
+template <int NP, int RB, int CB>
+__global__ void __launch_bounds__(MT<NP, RB, CB>::WARPS == 1 ? 128 : MT<NP, RB, CB>::THREADS)
+k_expm_mma(QocParams p) {
+  typedef MT<NP, RB, CB> T_;
+  constexpr int WARPS = T_::WARPS;
+  constexpr int G = T_::THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ipc = WARPS == 1 ? 4 : 1;                 // items per CTA
+  const int slot = WARPS == 1 ? (threadIdx.x >> 5) : 0;
+  const int gt = WARPS == 1 ? (threadIdx.x & 31) : threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = WARPS == 1 ? 0 : (threadIdx.x >> 5);
+  const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
+  const size_t item_bytes = (size_t)3 * T_::MAT * sizeof(cplx) + 32 * sizeof(double);
+  cplx* Hs = reinterpret_cast<cplx*>(smem_raw + slot * item_bytes);
+  cplx* buf1 = Hs + T_::MAT;
+  cplx* buf2 = buf1 + T_::MAT;
+  double* wts = reinterpret_cast<double*>(buf2 + T_::MAT);
+  const int n = p.n, K = p.K, T = p.T, nn = n * n;
+  const int ksteps = (n + 3) >> 2;
+  const long long items = (long long)p.B * T;
+  cplx* Pout = reinterpret_cast<cplx*>(p.P);
+  const int g = lane >> 2, q = lane & 3;
+
+  for (int i = gt; i < 3 * T_::MAT; i += G) Hs[i] = make_double2(0.0, 0.0);   // padding stays zero forever
+  item_sync<WARPS>();
+
+  for (long long item = (long long)blockIdx.x * ipc + slot; item < items; item += (long long)gridDim.x * ipc) {
+    const int b = (int)(item / T), t = (int)(item % T);
+    // u_k(t)/2^s with u_k = maxA_k sin(base) (tensorflow_state.py:31,176-178); weight 0 = drift
+    if (gt == 0) wts[0] = p.inv2s;
+    if (gt >= 1 && gt <= K) wts[gt] = p.maxA[gt - 1] * sin(p.base[((size_t)b * K + gt - 1) * T + t]) * p.inv2s;
+    item_sync<WARPS>();
+    // H assembly over the union sparsity pattern of A_0..A_K (entries outside it are never written)
+    for (int e = gt; e < p.pat_n; e += G) {
+      const int rc = p.pat_rc[e];
+      const cplx* cf = p.pat_coef + (size_t)e * (K + 1);
+      double hx = 0.0, hy = 0.0;
+      for (int k = 0; k <= K; ++k) {
+        const cplx a = cf[k];
+        const double w = wts[k];
+        hx = fma(w, a.x, hx); hy = fma(w, a.y, hy);
+      }
+      Hs[swz<NP>(rc >> 16, rc & 0xffff)] = make_double2(hx, hy);
+    }
+    item_sync<WARPS>();
+
+    // Taylor: S = I + H + sum_{j=2..p} term_j, term_j = H term_{j-1} / j   (tensorflow_state.py:37-41)
+    double sr[RB][CB][2], si[RB][CB][2], cr[RB][CB][2], ci[RB][CB][2];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = 8 * (rb0 + i) + g;
+#pragma unroll
+      for (int j = 0; j < CB; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 8 * (cb0 + j) + 2 * q + e;
+          const cplx h = Hs[swz<NP>(r, c)];
+          sr[i][j][e] = h.x + ((r == c && r < n) ? 1.0 : 0.0);
+          si[i][j][e] = h.y;
+        }
+    }
+    const cplx* cur = Hs;
+    cplx* nxt = buf1;
+    for (int j = 2; j <= p.p; ++j) {
+      mma_gemm<NP, RB, CB>(Hs, cur, cr, ci, rb0, cb0, ksteps, lane);
+      const double inv = 1.0 / (double)j;
+#pragma unroll
+      for (int i = 0; i < RB; ++i)
+#pragma unroll
+        for (int jj = 0; jj < CB; ++jj)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            cr[i][jj][e] *= inv; ci[i][jj][e] *= inv;
+            sr[i][jj][e] += cr[i][jj][e]; si[i][jj][e] += ci[i][jj][e];
+          }
+      if (j < p.p) {
+        store_tile<NP, RB, CB>(nxt, cr, ci, rb0, cb0, lane);
+        item_sync<WARPS>();
+        cur = nxt;
+        nxt = (nxt == buf1) ? buf2 : buf1;
+      }
+    }
+    // squarings (tensorflow_state.py:43-44)
+    {
+      cplx* X = nxt;                       // not an operand of the last Taylor product
+      cplx* Y = (X == buf1) ? buf2 : buf1;
+      for (int s = 0; s < p.s; ++s) {
+        store_tile<NP, RB, CB>(X, sr, si, rb0, cb0, lane);
+        item_sync<WARPS>();
+        mma_gemm<NP, RB, CB>(X, X, sr, si, rb0, cb0, ksteps, lane);
+        cplx* tmp = X; X = Y; Y = tmp;
+      }
+    }
+    cplx* dst = Pout + (size_t)item * nn;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = 8 * (rb0 + i) + g;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) {
+        const int c = 8 * (cb0 + j) + 2 * q;
+        if (r < n && c < n) dst[r * n + c] = make_double2(sr[i][j][0], si[i][j][0]);
+        if (r < n && c + 1 < n) dst[r * n + c + 1] = make_double2(sr[i][j][1], si[i][j][1]);
+      }
+    }
+    item_sync<WARPS>();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_chain_mma: one CTA per instance; X resident in shared memory (ping-pong), P_t streamed with
+// cp.async into NPB swizzled buffers (prefetch distance NPB-1).
+// ---------------------------------------------------------------------------------------------
+template <int NP, int RB, int CB, int NPB, int NXB>
+__global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams p) {
+  typedef MT<NP, RB, CB> T_;
+  constexpr int G = T_::THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* Pb = reinterpret_cast<cplx*>(smem_raw);           // [NPB][MAT]
+  cplx* Xb = Pb + NPB * T_::MAT;                          // [NXB][MAT]
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
+  const int n = p.n, T = p.T, m = p.m, nn = n * n;
+  const int ksteps = (n + 3) >> 2;
+  const int b = blockIdx.x;
+  const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * nn;
+  cplx* psi_b = p.psi + (size_t)b * (T + 1) * m * n;
+
+  for (int i = tid; i < (NPB + NXB) * T_::MAT; i += G) Pb[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int idx = tid; idx < nn; idx += G) {
+    const int r = idx / n, c = idx - r * n;
+    Xb[swz<NP>(r, c)] = p.U0[idx];
+  }
+  for (int idx = tid; idx < m * n; idx += G) psi_b[idx] = p.V[idx];     // inter_vecs[0] = V (:233-234)
+
+  auto prefetch = [&](int t) {
+    if (t < T) {
+      const cplx* src = Pg + (size_t)t * nn;
+      cplx* dst = Pb + (t % NPB) * T_::MAT;
+      for (int idx = tid; idx < nn; idx += G) {
+        const int r = idx / n, c = idx - r * n;
+        cp_async16(dst + swz<NP>(r, c), src + idx);
+      }
+    }
+    cp_async_commit();
+  };
+  auto extract = [&](const cplx* X, int t) {              // psi[t][j][i] = (X V)_ij
+    cplx* out = psi_b + (size_t)t * m * n;
+    if (p.has_cidx) {
+      for (int idx = tid; idx < m * n; idx += G) {
+        const int j = idx / n, i = idx - j * n;
+        out[idx] = X[swz<NP>(i, p.cidx[j])];
+      }
+    } else {
+      for (int idx = tid; idx < m * n; idx += G) {
+        const int j = idx / n, i = idx - j * n;
+        double ax = 0.0, ay = 0.0;
+        for (int c = 0; c < n; ++c) {
+          const cplx x = X[swz<NP>(i, c)], v = p.V[j * n + c];
+          ax += x.x * v.x - x.y * v.y; ay += x.x * v.y + x.y * v.x;
+        }
+        out[idx] = make_double2(ax, ay);
+      }
+    }
+  };
+
+#pragma unroll
+  for (int i = 0; i < NPB - 1; ++i) prefetch(i);
+  for (int t = 0; t < T; ++t) {
+    cp_async_wait<NPB - 2>();
+    __syncthreads();                                  // P_t landed; X_t complete; step t-1 reads done
+    const cplx* Xc = Xb + (NXB == 2 ? (t & 1) : 0) * T_::MAT;
+    cplx* Xn = Xb + (NXB == 2 ? ((t + 1) & 1) : 0) * T_::MAT;
+    if (t > 0) extract(Xc, t);
+    prefetch(t + NPB - 1);
+    double cr[RB][CB][2], ci[RB][CB][2];
+    mma_gemm<NP, RB, CB>(Pb + (t % NPB) * T_::MAT, Xc, cr, ci, rb0, cb0, ksteps, lane);
+    if (NXB == 1) __syncthreads();                    // in-place update: every warp has finished reading X
+    store_tile<NP, RB, CB>(Xn, cr, ci, rb0, cb0, lane);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const cplx* Xf = Xb + (NXB == 2 ? (T & 1) : 0) * T_::MAT;
+  extract(Xf, T);
+  cplx* Uf = p.Ufin + (size_t)b * nn;
+  for (int idx = tid; idx < nn; idx += G) {
+    const int r = idx / n, c = idx - r * n;
+    Uf[idx] = Xf[swz<NP>(r, c)];
+  }
+  // unitary_scale = (0.5/n) sum_ab (X^T X)_ab over the real embedding = (1/n) sum_r |sum_c X_rc|^2 (:225)
+  double v = 0.0;
+  for (int r = tid; r < n; r += G) {
+    double sr = 0.0, si = 0.0;
+    for (int c = 0; c < n; ++c) { const cplx x = Xf[swz<NP>(r, c)]; sr += x.x; si += x.y; }
+    v += sr * sr + si * si;
+  }
+  v = warp_sum_d(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < T_::WARPS; ++w) s += red[w];
+    p.scal[(size_t)b * 8 + 5] = s / (double)n;
+  }
+}
+
+template <int NP, int RB, int CB>
+cudaError_t launch_expm(const QocParams& p, int sm_count, cudaStream_t st) {
+  typedef MT<NP, RB, CB> T_;
+  const int ipc = T_::WARPS == 1 ? 4 : 1;
+  const int threads = T_::WARPS == 1 ? 128 : T_::THREADS;
+  const size_t smem = ((size_t)3 * T_::MAT * sizeof(cplx) + 32 * sizeof(double)) * ipc;
+  cudaError_t e = cudaFuncSetAttribute(k_expm_mma<NP, RB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expm_mma<NP, RB, CB>, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const long long items = (long long)p.B * p.T;
+  long long grid = (long long)sm_count * occ;
+  const long long need = (items + ipc - 1) / ipc;
+  if (grid > need) grid = need;
+  k_expm_mma<NP, RB, CB><<<(unsigned)grid, threads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int NP, int RB, int CB, int NPB, int NXB>
+cudaError_t launch_chain(const QocParams& p, cudaStream_t st) {
+  typedef MT<NP, RB, CB> T_;
+  const size_t smem = (size_t)(NPB + NXB) * T_::MAT * sizeof(cplx);
+  cudaError_t e = cudaFuncSetAttribute(k_chain_mma<NP, RB, CB, NPB, NXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_chain_mma<NP, RB, CB, NPB, NXB><<<p.B, T_::THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches) {
+  ++*launches;
+  switch (NP) {
+    case 8: return launch_expm<8, 1, 1>(p, sm_count, st);
+    case 16: return launch_expm<16, 2, 2>(p, sm_count, st);
+    case 24: return launch_expm<24, 1, 3>(p, sm_count, st);
+    case 32: return launch_expm<32, 2, 4>(p, sm_count, st);
+    case 40: return launch_expm<40, 1, 5>(p, sm_count, st);
+    case 48: return launch_expm<48, 2, 3>(p, sm_count, st);
+    case 56: return launch_expm<56, 1, 7>(p, sm_count, st);
+    case 64: return launch_expm<64, 2, 4>(p, sm_count, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, cudaStream_t st, int64_t* launches) {
+  ++*launches;
+  switch (NP) {
+    case 8: return launch_chain<8, 1, 1, 3, 2>(p, st);
+    case 16: return launch_chain<16, 1, 1, 3, 2>(p, st);
+    case 24: return launch_chain<24, 1, 1, 3, 2>(p, st);
+    case 32: return launch_chain<32, 1, 2, 3, 2>(p, st);
+    case 40: return launch_chain<40, 1, 5, 3, 2>(p, st);
+    case 48: return launch_chain<48, 1, 3, 3, 2>(p, st);
+    case 56: return launch_chain<56, 1, 7, 2, 2>(p, st);      // 4 x 50 KB
+    case 64: return launch_chain<64, 2, 4, 2, 1>(p, st);      // 3 x 64 KB: X updated in place
+  }
+  return cudaErrorInvalidValue;
+}

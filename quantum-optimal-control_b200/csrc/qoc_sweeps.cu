@@ -1,9 +1,6 @@
-// FP64 kernels of the GRAPE hot path (sm_100a).
+// Sweep / reduction kernels of the GRAPE hot path (sm_100a); the GEMM-shaped stages (propagator
+// exponentials and the forward chain) live in qoc_mma_f64.cu.
 //
-//   k_expm      : (b,t) -> P_t = (sum_{j<=p} H^j/j!)^(2^s),  H = (A_0 + sum_k u_k(t) A_k)/2^s
-//                 replaces get_matexp / matexp_op   (core/tensorflow_state.py:25-46,70-75)
-//   k_chain     : b -> X_t = P_t X_{t-1}, psi_j(t+1) = X_t V_j, U_final, unitary_scale
-//                 replaces init_tf_propagator / init_tf_inter_vectors (:204-242)
 //   k_fwd_reduce: b -> overlap, loss, forbidden / speed_up values (:282-321,:323-329,
 //                 core/regularization_functions.py:71-95)
 //   k_costate   : b -> lambda(t) = P_t^dagger lambda(t+1) + sources(t); the reverse sweep TF autodiff
@@ -67,249 +64,6 @@ DEVINL void cp_async16(void* smem_dst, const void* gmem_src) {
 DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// ---------------------------------------------------------------------------------------------
-// Register-tiled complex GEMM on shared-memory operands.
-// A group of G = (NP/TM)*(NP/TN) threads owns one NP x NP product; thread (ty,tx) owns rows
-// ty + i*TY and columns tx + j*TX (interleaved so that b-loads of a warp are contiguous and
-// a-loads are broadcasts).  Operand leading dimension LD = NP+1 complex (bank spread).
-// ---------------------------------------------------------------------------------------------
-template <int NP, int TM, int TN>
-struct Tile {
-  static constexpr int TY = NP / TM;
-  static constexpr int TX = NP / TN;
-  static constexpr int G = TX * TY;
-  static constexpr int LD = NP + 1;
-  static constexpr int MAT = NP * LD;   // complex elements per padded matrix
-};
-
-template <int NP, int TM, int TN>
-DEVINL void gemm_tile(const cplx* __restrict__ As, const cplx* __restrict__ Bs, cplx (&acc)[TM][TN],
-                      int ty, int tx, int kdim) {
-  typedef Tile<NP, TM, TN> TL;
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = make_double2(0.0, 0.0);
-#pragma unroll 2
-  for (int k = 0; k < kdim; ++k) {
-    cplx a[TM], b[TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) a[i] = As[(ty + i * TL::TY) * TL::LD + k];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) b[j] = Bs[k * TL::LD + tx + j * TL::TX];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) cfma(acc[i][j], a[i], b[j]);
-  }
-}
-
-template <int G>
-DEVINL void group_sync() {
-  if (G <= 32) __syncwarp(); else __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_expm: persistent over (b,t) items.  CTA = GPC groups of G threads; each group has 3 padded
-// matrices in shared memory (H, ping, pong) + K weights.
-// ---------------------------------------------------------------------------------------------
-template <int NP, int TM, int TN>
-__global__ void k_expm(QocParams p) {
-  typedef Tile<NP, TM, TN> TL;
-  constexpr int G = TL::G;
-  constexpr int LD = TL::LD;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int gpc = blockDim.x / G;                 // groups per CTA
-  const int grp = threadIdx.x / G;
-  const int gt = threadIdx.x % G;
-  const int ty = gt / TL::TX, tx = gt % TL::TX;
-  const size_t grp_bytes = (size_t)3 * TL::MAT * sizeof(cplx) + 32 * sizeof(double);
-  cplx* Hs = reinterpret_cast<cplx*>(smem_raw + grp * grp_bytes);
-  cplx* buf1 = Hs + TL::MAT;
-  cplx* buf2 = buf1 + TL::MAT;
-  double* wts = reinterpret_cast<double*>(buf2 + TL::MAT);
-  const int n = p.n, K = p.K, T = p.T;
-  const int nn = n * n;
-  const long long items = (long long)p.B * T;
-  cplx* Pout = reinterpret_cast<cplx*>(p.P);
-
-  // zero the three buffers once: padding stays zero for the whole kernel
-  for (int i = gt; i < 3 * TL::MAT; i += G) Hs[i] = make_double2(0.0, 0.0);
-  group_sync<G>();
-
-  for (long long item = (long long)blockIdx.x * gpc + grp; item < items; item += (long long)gridDim.x * gpc) {
-    const int b = (int)(item / T), t = (int)(item % T);
-    // control amplitudes u_k(t) = maxA_k sin(base) (tensorflow_state.py:176-178), pre-divided by 2^s (:31)
-    if (gt < K) wts[gt] = p.maxA[gt] * sin(p.base[((size_t)b * K + gt) * T + t]) * p.inv2s;
-    group_sync<G>();
-    for (int idx = gt; idx < nn; idx += G) {
-      const int r = idx / n, c = idx - r * n;
-      cplx v = p.A[idx];
-      v.x *= p.inv2s; v.y *= p.inv2s;
-      for (int k = 0; k < K; ++k) {
-        const cplx a = p.A[(size_t)(k + 1) * nn + idx];
-        const double w = wts[k];
-        v.x = fma(w, a.x, v.x); v.y = fma(w, a.y, v.y);
-      }
-      Hs[r * LD + c] = v;
-    }
-    group_sync<G>();
-
-    // Taylor: S = I + H + sum_{j=2..p} H^j/j!, term_j = H * term_{j-1} / j
-    cplx S[TM][TN], C[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int r = ty + i * TL::TY, c = tx + j * TL::TX;
-        S[i][j] = Hs[r * LD + c];
-        if (r == c && r < n) S[i][j].x += 1.0;
-      }
-    const cplx* cur = Hs;
-    cplx* nxt = buf1;
-    for (int j = 2; j <= p.p; ++j) {
-      gemm_tile<NP, TM, TN>(Hs, cur, C, ty, tx, n);
-      const double inv = 1.0 / (double)j;
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int jj = 0; jj < TN; ++jj) {
-          C[i][jj].x *= inv; C[i][jj].y *= inv;
-          S[i][jj].x += C[i][jj].x; S[i][jj].y += C[i][jj].y;
-        }
-      if (j < p.p) {
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int jj = 0; jj < TN; ++jj) nxt[(ty + i * TL::TY) * LD + tx + jj * TL::TX] = C[i][jj];
-        group_sync<G>();
-        cur = nxt;
-        nxt = (nxt == buf1) ? buf2 : buf1;
-      }
-    }
-    // squarings (tensorflow_state.py:43-44)
-    if (p.s > 0) {
-      cplx* X = nxt;                       // not read by the last Taylor product
-      cplx* Y = (X == buf1) ? buf2 : buf1;
-      if (p.p < 2) group_sync<G>();
-      for (int q = 0; q < p.s; ++q) {
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int jj = 0; jj < TN; ++jj) X[(ty + i * TL::TY) * LD + tx + jj * TL::TX] = S[i][jj];
-        group_sync<G>();
-        gemm_tile<NP, TM, TN>(X, X, S, ty, tx, n);
-        cplx* tmp = X; X = Y; Y = tmp;
-      }
-    }
-    cplx* dst = Pout + (size_t)item * nn;
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int r = ty + i * TL::TY;
-#pragma unroll
-      for (int jj = 0; jj < TN; ++jj) {
-        const int c = tx + jj * TL::TX;
-        if (r < n && c < n) dst[r * n + c] = S[i][jj];
-      }
-    }
-    group_sync<G>();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_chain: one CTA (= one group) per instance; X resident in shared memory, P_t streamed with
-// cp.async (3 buffers, prefetch distance 2).
-// ---------------------------------------------------------------------------------------------
-template <int NP, int TM, int TN, int NPB, int NXB>
-__global__ void k_chain(QocParams p) {
-  typedef Tile<NP, TM, TN> TL;
-  constexpr int G = TL::G;
-  constexpr int LD = TL::LD;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* Pb = reinterpret_cast<cplx*>(smem_raw);           // [NPB][MAT]
-  cplx* Xb = Pb + NPB * TL::MAT;                          // [NXB][MAT]
-  __shared__ double red[64];
-  const int tid = threadIdx.x;
-  const int ty = tid / TL::TX, tx = tid % TL::TX;
-  const int n = p.n, T = p.T, m = p.m;
-  const int nn = n * n;
-  const int b = blockIdx.x;
-  const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * nn;
-  cplx* psi_b = p.psi + (size_t)b * (T + 1) * m * n;
-
-  for (int i = tid; i < (NPB + NXB) * TL::MAT; i += G) Pb[i] = make_double2(0.0, 0.0);
-  __syncthreads();
-  for (int idx = tid; idx < nn; idx += G) {
-    const int r = idx / n, c = idx - r * n;
-    Xb[r * LD + c] = p.U0[idx];
-  }
-  for (int idx = tid; idx < m * n; idx += G) psi_b[idx] = p.V[idx];     // inter_vecs[0] = V (:233-234)
-
-  auto prefetch = [&](int t) {
-    if (t < T) {
-      const cplx* src = Pg + (size_t)t * nn;
-      cplx* dst = Pb + (t % NPB) * TL::MAT;
-      for (int idx = tid; idx < nn; idx += G) {
-        const int r = idx / n, c = idx - r * n;
-        cp_async16(dst + r * LD + c, src + idx);
-      }
-    }
-    cp_async_commit();
-  };
-  auto extract = [&](const cplx* X, int t) {     // psi[t][j][i] = (X V)_ij
-    cplx* out = psi_b + (size_t)t * m * n;
-    if (p.has_cidx) {
-      for (int idx = tid; idx < m * n; idx += G) {
-        const int j = idx / n, i = idx - j * n;
-        out[idx] = X[i * LD + p.cidx[j]];
-      }
-    } else {
-      for (int idx = tid; idx < m * n; idx += G) {
-        const int j = idx / n, i = idx - j * n;
-        cplx acc = make_double2(0.0, 0.0);
-        for (int c = 0; c < n; ++c) cfma(acc, X[i * LD + c], p.V[j * n + c]);
-        out[idx] = acc;
-      }
-    }
-  };
-
-#pragma unroll
-  for (int i = 0; i < NPB - 1; ++i) prefetch(i);
-  for (int t = 0; t < T; ++t) {
-    cp_async_wait<NPB - 2>();
-    __syncthreads();                                  // P_t landed; X_t complete; step t-1 reads done
-    const cplx* Xc = Xb + (NXB == 2 ? (t & 1) : 0) * TL::MAT;
-    cplx* Xn = Xb + (NXB == 2 ? ((t + 1) & 1) : 0) * TL::MAT;
-    if (t > 0) extract(Xc, t);
-    prefetch(t + NPB - 1);
-    cplx C[TM][TN];
-    gemm_tile<NP, TM, TN>(Pb + (t % NPB) * TL::MAT, Xc, C, ty, tx, n);
-    if (NXB == 1) __syncthreads();                    // in-place update: everyone has finished reading X
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int jj = 0; jj < TN; ++jj) Xn[(ty + i * TL::TY) * LD + tx + jj * TL::TX] = C[i][jj];
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-  const cplx* Xf = Xb + (NXB == 2 ? (T & 1) : 0) * TL::MAT;
-  extract(Xf, T);
-  cplx* Uf = p.Ufin + (size_t)b * nn;
-  for (int idx = tid; idx < nn; idx += G) {
-    const int r = idx / n, c = idx - r * n;
-    Uf[idx] = Xf[r * LD + c];
-  }
-  // unitary_scale = (0.5/n) sum_ab (X^T X)_ab over the real embedding = (1/n) sum_r |sum_c X_rc|^2 (:225)
-  double v[1] = {0.0};
-  for (int r = tid; r < n; r += G) {
-    double sr = 0.0, si = 0.0;
-    for (int c = 0; c < n; ++c) { sr += Xf[r * LD + c].x; si += Xf[r * LD + c].y; }
-    v[0] += sr * sr + si * si;
-  }
-  block_sum<1>(v, red);
-  if (tid == 0) p.scal[(size_t)b * 8 + 5] = v[0] / (double)n;
-}
 
 // ---------------------------------------------------------------------------------------------
 // k_fwd_reduce: one CTA per instance; a warp per time step.
@@ -563,61 +317,6 @@ __global__ void k_finalize(QocParams p) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-template <int NP, int TM, int TN>
-static cudaError_t launch_expm_cfg(const QocParams& p, int sm_count, cudaStream_t st) {
-  typedef Tile<NP, TM, TN> TL;
-  constexpr int G = TL::G;
-  const int gpc = G >= 64 ? 1 : 128 / G;
-  const size_t grp_bytes = (size_t)3 * TL::MAT * sizeof(cplx) + 32 * sizeof(double);
-  const size_t smem = grp_bytes * gpc;
-  cudaError_t e = cudaFuncSetAttribute(k_expm<NP, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expm<NP, TM, TN>, G * gpc, smem);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) occ = 1;
-  const long long items = (long long)p.B * p.T;
-  long long grid = (long long)sm_count * occ;
-  const long long need = (items + gpc - 1) / gpc;
-  if (grid > need) grid = need;
-  k_expm<NP, TM, TN><<<(unsigned)grid, G * gpc, smem, st>>>(p);
-  return cudaGetLastError();
-}
-
-cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches) {
-  ++*launches;
-  switch (NP) {
-    case 8: return launch_expm_cfg<8, 1, 2>(p, sm_count, st);
-    case 16: return launch_expm_cfg<16, 2, 4>(p, sm_count, st);
-    case 32: return launch_expm_cfg<32, 4, 4>(p, sm_count, st);
-    case 48: return launch_expm_cfg<48, 3, 4>(p, sm_count, st);
-    case 64: return launch_expm_cfg<64, 4, 4>(p, sm_count, st);
-  }
-  return cudaErrorInvalidValue;
-}
-
-template <int NP, int TM, int TN, int NPB, int NXB>
-static cudaError_t launch_chain_cfg(const QocParams& p, cudaStream_t st) {
-  typedef Tile<NP, TM, TN> TL;
-  const size_t smem = (size_t)(NPB + NXB) * TL::MAT * sizeof(cplx);
-  cudaError_t e = cudaFuncSetAttribute(k_chain<NP, TM, TN, NPB, NXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k_chain<NP, TM, TN, NPB, NXB><<<p.B, TL::G, smem, st>>>(p);
-  return cudaGetLastError();
-}
-
-cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, cudaStream_t st, int64_t* launches) {
-  ++*launches;
-  switch (NP) {
-    case 8: return launch_chain_cfg<8, 1, 2, 3, 2>(p, st);
-    case 16: return launch_chain_cfg<16, 1, 2, 3, 2>(p, st);
-    case 32: return launch_chain_cfg<32, 2, 2, 3, 2>(p, st);
-    case 48: return launch_chain_cfg<48, 3, 2, 3, 2>(p, st);
-    case 64: return launch_chain_cfg<64, 4, 4, 2, 1>(p, st);   // 3 x 66.5 KB: P double-buffered, X updated in place
-  }
-  return cudaErrorInvalidValue;
-}
-
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches) {
   ++*launches;
   k_fwd_reduce<<<p.B, 256, 0, st>>>(p);

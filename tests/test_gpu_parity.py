@@ -29,7 +29,9 @@ CASES = {
     'c3_T30': (lambda: W.c3_two_transmon_cnot(T=30), dict(total_time=0.3), 2),
     'c5_n8': (lambda: W.c5_random(8, T=20), {}, 2),
     'c5_n16': (lambda: W.c5_random(16, T=20), {}, 2),
+    'c5_n20': (lambda: W.c5_random(20, T=12), {}, 2),
     'c5_n48': (lambda: W.c5_random(48, T=6), {}, 1),
+    'c5_n50': (lambda: W.c5_random(50, T=5), {}, 1),
     'c5_n64': (lambda: W.c5_random(64, T=5), {}, 1),
     'n5_U0': (lambda: W.c5_random(5, T=15), dict(U0=np.linalg.qr(np.random.default_rng(5).normal(size=(5, 5)) +
                                                                   1j * np.random.default_rng(6).normal(size=(5, 5)))[0],
