@@ -12,6 +12,7 @@ struct QocParams {
   int n, K, T, m, B, p, s;
   int has_cidx;
   double dt, inv2s;
+  double invfact[32];   // 1/j!
   // constants
   const cplx* A;        // [K+1][n][n]
   const cplx* U0;       // [n][n]

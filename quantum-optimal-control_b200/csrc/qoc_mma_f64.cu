@@ -179,47 +179,65 @@ k_expm_mma(QocParams p) {
     }
     item_sync<WARPS>();
 
-    // Taylor: S = I + H + sum_{j=2..p} term_j, term_j = H term_{j-1} / j   (tensorflow_state.py:37-41)
-    double sr[RB][CB][2], si[RB][CB][2], cr[RB][CB][2], ci[RB][CB][2];
+    // Taylor polynomial S = sum_{j<=p} H^j/j! (tensorflow_state.py:37-41), evaluated in
+    // Paterson-Stockmeyer form with block size 2: S = (..(B_r H2 + B_{r-1}) H2 + ..) H2 + B_0,
+    // B_i = c_{2i} I + c_{2i+1} H, c_j = 1/j!  -> 1 + floor(p/2) - [p even] products instead of p-1.
+    double sr[RB][CB][2], si[RB][CB][2];
+    auto add_block = [&](double c_id, double c_h, bool init) {     // S (+)= c_id*I + c_h*H on this lane's fragments
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int r = 8 * (rb0 + i) + g;
+      for (int i = 0; i < RB; ++i) {
+        const int r = 8 * (rb0 + i) + g;
 #pragma unroll
-      for (int j = 0; j < CB; ++j)
+        for (int j = 0; j < CB; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = 8 * (cb0 + j) + 2 * q + e;
-          const cplx h = Hs[swz<NP>(r, c)];
-          sr[i][j][e] = h.x + ((r == c && r < n) ? 1.0 : 0.0);
-          si[i][j][e] = h.y;
-        }
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * (cb0 + j) + 2 * q + e;
+            const cplx h = Hs[swz<NP>(r, c)];
+            const double vr = c_h * h.x + ((r == c && r < n) ? c_id : 0.0), vi = c_h * h.y;
+            if (init) { sr[i][j][e] = vr; si[i][j][e] = vi; }
+            else { sr[i][j][e] += vr; si[i][j][e] += vi; }
+          }
+      }
+    };
+    const int pp = p.p;
+    cplx* H2 = buf1;
+    cplx* Rb = buf2;
+    if (pp >= 2) {
+      mma_gemm<NP, RB, CB>(Hs, Hs, sr, si, rb0, cb0, ksteps, lane);
+      store_tile<NP, RB, CB>(H2, sr, si, rb0, cb0, lane);
+      item_sync<WARPS>();
     }
-    const cplx* cur = Hs;
-    cplx* nxt = buf1;
-    for (int j = 2; j <= p.p; ++j) {
-      mma_gemm<NP, RB, CB>(Hs, cur, cr, ci, rb0, cb0, ksteps, lane);
-      const double inv = 1.0 / (double)j;
+    int blk;
+    if (pp & 1) {                                   // top block B_r = c_{p-1} I + c_p H
+      add_block(p.invfact[pp - 1], p.invfact[pp], true);
+      blk = pp / 2 - 1;
+    } else {                                        // top block is c_p I: first Horner step needs no product
+      const double cp = p.invfact[pp];
 #pragma unroll
       for (int i = 0; i < RB; ++i)
 #pragma unroll
-        for (int jj = 0; jj < CB; ++jj)
+        for (int j = 0; j < CB; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            cr[i][jj][e] *= inv; ci[i][jj][e] *= inv;
-            sr[i][jj][e] += cr[i][jj][e]; si[i][jj][e] += ci[i][jj][e];
-          }
-      if (j < p.p) {
-        store_tile<NP, RB, CB>(nxt, cr, ci, rb0, cb0, lane);
-        item_sync<WARPS>();
-        cur = nxt;
-        nxt = (nxt == buf1) ? buf2 : buf1;
-      }
+          for (int e = 0; e < 2; ++e) { sr[i][j][e] *= cp; si[i][j][e] *= cp; }     // sr/si hold H2 here
+      add_block(p.invfact[pp - 2], p.invfact[pp - 1], false);
+      blk = pp / 2 - 2;
+    }
+    for (; blk >= 0; --blk) {
+      // R <- R * H2 + B_blk.  R is the A operand: a warp only reads the rows it owns when it spans
+      // all block columns (WC == 1), so the in-place round trip through Rb needs no CTA barrier then.
+      if (T_::WC == 1) __syncwarp(); else __syncthreads();
+      store_tile<NP, RB, CB>(Rb, sr, si, rb0, cb0, lane);
+      if (T_::WC == 1) __syncwarp(); else __syncthreads();
+      mma_gemm<NP, RB, CB>(Rb, H2, sr, si, rb0, cb0, ksteps, lane);
+      add_block(p.invfact[2 * blk], p.invfact[2 * blk + 1], false);
     }
     // squarings (tensorflow_state.py:43-44)
-    {
-      cplx* X = nxt;                       // not an operand of the last Taylor product
-      cplx* Y = (X == buf1) ? buf2 : buf1;
+    if (p.s > 0) {
+      cplx* X = Rb;
+      cplx* Y = H2;
+      if (T_::WC != 1) __syncthreads();             // other warps may still read Rb rows they do not own
       for (int s = 0; s < p.s; ++s) {
+        if (T_::WC == 1 && s == 0) __syncwarp();
         store_tile<NP, RB, CB>(X, sr, si, rb0, cb0, lane);
         item_sync<WARPS>();
         mma_gemm<NP, RB, CB>(X, X, sr, si, rb0, cb0, ksteps, lane);
