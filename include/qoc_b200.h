@@ -146,6 +146,10 @@ int qoc_debug_propagators(qoc_handle_t h, void** P_dev, int* elem_bytes);
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t qoc_launch_count(qoc_handle_t h);
 
+/* Synchronises `stream` and reports device-side failures that cannot surface through a launch status
+ * (the tcgen05 pipeline bails out instead of hanging if an MMA completion barrier never fires). */
+int qoc_poll_error(qoc_handle_t h, void* stream);
+
 /* Optional per-kernel timing with CUDA events recorded on the call's stream around each of the
  * QOC_NUM_KERNELS launches of the last qoc_value_and_grad (order: expm, chain, fwd_reduce, costate,
  * grad, finalize).  qoc_kernel_times_ms synchronises on the last event. */

@@ -18,9 +18,10 @@ struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, s
 static WsLayout ws_layout(const qoc_dims_t& d) {
   WsLayout L;
   const size_t nn = (size_t)d.n * d.n, mn = (size_t)d.m * d.n;
-  const size_t pel = d.dtype == QOC_F64 ? sizeof(cplx) : sizeof(float2);
+  // propagators: fp64 interleaved [n][n] complex, or (QOC_TF32X3) fp32 planar padded [2][32][32]
+  const size_t p_item = d.dtype == QOC_F64 ? nn * sizeof(cplx) : (size_t)2 * 32 * 32 * sizeof(float);
   size_t off = 0;
-  L.P = off; off += align_up((size_t)d.B * d.T * nn * pel);
+  L.P = off; off += align_up((size_t)d.B * d.T * p_item);
   L.psi = off; off += align_up((size_t)d.B * (d.T + 1) * mn * sizeof(cplx));
   L.lam = off; off += align_up((size_t)d.B * (d.T + 1) * mn * sizeof(cplx));
   L.gctrl = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
@@ -52,6 +53,7 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   h->NP = pick_np(d.n);
   h->problem_set = h->ws_set = false;
   h->A = h->U0 = h->phi = h->V = h->coo_v = h->pat_coef = nullptr;
+  h->pat_coef_f = nullptr; h->err_flag = nullptr;
   h->cidx = h->coo_off = h->coo_r = h->coo_c = h->pat_rc = nullptr;
   h->pat_n = 0;
   h->maxA = h->env = h->fw = nullptr;
@@ -74,9 +76,12 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
     h->err = "QOC_F64 supports n <= 64";
     return QOC_EINVAL;
   }
-  if (d.dtype == QOC_TF32X3) {
-    h->err = "QOC_TF32X3 is not available in this build";
+  if (d.dtype == QOC_TF32X3 && (d.n > 32 || d.K > 15)) {
+    h->err = "QOC_TF32X3 (tcgen05 path) supports n <= 32, K <= 15 in this build";
     return QOC_EINVAL;
+  }
+  if (cudaMalloc((void**)&h->err_flag, sizeof(int)) != cudaSuccess || cudaMemset(h->err_flag, 0, sizeof(int)) != cudaSuccess) {
+    h->err = "cudaMalloc failed"; return QOC_ECUDA;
   }
   return QOC_OK;
 }
@@ -85,7 +90,7 @@ int qoc_destroy(qoc_handle_t h) {
   QOC_CHECK_H(h);
   cudaFree(h->A); cudaFree(h->U0); cudaFree(h->phi); cudaFree(h->V); cudaFree(h->coo_v);
   cudaFree(h->cidx); cudaFree(h->coo_off); cudaFree(h->coo_r); cudaFree(h->coo_c);
-  cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw); cudaFree(h->pat_rc); cudaFree(h->pat_coef);
+  cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw); cudaFree(h->pat_rc); cudaFree(h->pat_coef); cudaFree(h->pat_coef_f); cudaFree(h->err_flag);
   for (int i = 0; i <= QOC_NUM_KERNELS; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return QOC_OK;
@@ -176,6 +181,8 @@ int qoc_set_problem(qoc_handle_t h, const double* A_host, const double* U0_host,
   h->pat_n = (int)prc.size();
   CUDA_TRY(h, upload(&h->pat_rc, prc.data(), prc.size(), st));
   CUDA_TRY(h, upload(&h->pat_coef, pcf.data(), pcf.size() / 2, st));
+  std::vector<float> pcf32(pcf.begin(), pcf.end());
+  CUDA_TRY(h, upload(&h->pat_coef_f, pcf32.data(), pcf32.size() / 2, st));
   CUDA_TRY(h, upload(&h->A, A_host, (size_t)(d.K + 1) * nn, st));
   CUDA_TRY(h, upload(&h->U0, U0_host, nn, st));
   CUDA_TRY(h, upload(&h->phi, phi_host, mn, st));
@@ -225,7 +232,7 @@ static int fill_params(qoc_handle_t h, QocParams& p, const double* base) {
   p.A = h->A; p.U0 = h->U0; p.phi = h->phi; p.V = h->V; p.cidx = h->cidx; p.maxA = h->maxA;
   p.env = h->env; p.fw = h->fw;
   p.coo_off = h->coo_off; p.coo_r = h->coo_r; p.coo_c = h->coo_c; p.coo_v = h->coo_v;
-  p.pat_n = h->pat_n; p.pat_rc = h->pat_rc; p.pat_coef = h->pat_coef;
+  p.pat_n = h->pat_n; p.pat_rc = h->pat_rc; p.pat_coef = h->pat_coef; p.pat_coef_f = h->pat_coef_f;
   p.reg = h->reg;
   p.base = base;
   p.P = h->P; p.psi = h->psi; p.lam = h->lam; p.gctrl = h->gctrl; p.ot = h->ot; p.scal = h->scal; p.Ufin = h->Ufin;
@@ -245,9 +252,10 @@ static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   int rc;
   h->ev_recorded = 0;
   if ((rc = prof_mark(h, 0, st))) return rc;
-  CUDA_TRY(h, qoc_launch_expm_f64(p, h->NP, h->sm_count, st, &h->launches));
+  if (h->d.dtype == QOC_TF32X3) CUDA_TRY(h, qoc_launch_expm_tc32(p, h->sm_count, h->err_flag, st, &h->launches));
+  else CUDA_TRY(h, qoc_launch_expm_f64(p, h->NP, h->sm_count, st, &h->launches));
   if ((rc = prof_mark(h, 1, st))) return rc;
-  CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, st, &h->launches));
+  CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, h->d.dtype != QOC_F64, st, &h->launches));
   if ((rc = prof_mark(h, 2, st))) return rc;
   CUDA_TRY(h, qoc_launch_fwd_reduce(p, st, &h->launches));
   if ((rc = prof_mark(h, 3, st))) return rc;
@@ -354,6 +362,15 @@ int qoc_debug_propagators(qoc_handle_t h, void** P_dev, int* elem_bytes) {
 }
 
 int64_t qoc_launch_count(qoc_handle_t h) { return h ? h->launches : -1; }
+
+int qoc_poll_error(qoc_handle_t h, void* stream) {
+  QOC_CHECK_H(h);
+  int flag = 0;
+  CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+  CUDA_TRY(h, cudaMemcpy(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) { h->err = "tcgen05 pipeline timed out waiting for an MMA completion barrier"; return QOC_ECUDA; }
+  return QOC_OK;
+}
 
 int qoc_set_profiling(qoc_handle_t h, int enable) {
   QOC_CHECK_H(h);

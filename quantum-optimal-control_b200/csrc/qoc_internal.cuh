@@ -29,6 +29,7 @@ struct QocParams {
   int pat_n;            // union sparsity pattern of A_0..A_K
   const int* pat_rc;    // [pat_n]  (row << 16) | col
   const cplx* pat_coef; // [pat_n][K+1]
+  const float2* pat_coef_f;  // same in fp32 (tcgen05 path)
   qoc_reg_t reg;
   // per-call
   const double* base;   // [B][K][T]
@@ -52,6 +53,8 @@ struct qoc_handle_s {
   bool problem_set, ws_set;
   // device constants (cudaMalloc'd by the handle; a few hundred KB)
   cplx *A, *U0, *phi, *V, *coo_v, *pat_coef;
+  float2* pat_coef_f;
+  int* err_flag;
   int *cidx, *coo_off, *coo_r, *coo_c, *pat_rc;
   int pat_n;
   double *maxA, *env, *fw;
@@ -69,7 +72,8 @@ struct qoc_handle_s {
 
 // kernel launchers (qoc_mma_f64.cu, qoc_sweeps.cu); return cudaError_t, bump *launches
 cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);
-cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_expm_tc32(const QocParams& p, int sm_count, int* err_flag, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_grad(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches);

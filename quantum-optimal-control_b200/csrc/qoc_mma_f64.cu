@@ -263,13 +263,17 @@ k_expm_mma(QocParams p) {
 // k_chain_mma: one CTA per instance; X resident in shared memory (ping-pong), P_t streamed with
 // cp.async into NPB swizzled buffers (prefetch distance NPB-1).
 // ---------------------------------------------------------------------------------------------
-template <int NP, int RB, int CB, int NPB, int NXB>
+// PF32: propagators are the tcgen05 path's fp32 planar padded [2][32][32] tiles; they are streamed
+// raw into a staging ring and widened to double2 in the swizzled operand buffer each step.
+template <int NP, int RB, int CB, int NPB, int NXB, bool PF32>
 __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams p) {
   typedef MT<NP, RB, CB> T_;
   constexpr int G = T_::THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* Pb = reinterpret_cast<cplx*>(smem_raw);           // [NPB][MAT]
-  cplx* Xb = Pb + NPB * T_::MAT;                          // [NXB][MAT]
+  constexpr int NPBUF = PF32 ? 1 : NPB;                   // swizzled double2 operand buffers for P
+  cplx* Pb = reinterpret_cast<cplx*>(smem_raw);           // [NPBUF][MAT]
+  cplx* Xb = Pb + NPBUF * T_::MAT;                        // [NXB][MAT]
+  float* Pstage = reinterpret_cast<float*>(Xb + NXB * T_::MAT);   // PF32: [NPB][2048] raw fp32 tiles
   __shared__ double red[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
@@ -277,9 +281,10 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
   const int ksteps = (n + 3) >> 2;
   const int b = blockIdx.x;
   const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * nn;
+  const float* Pgf = reinterpret_cast<const float*>(p.P) + (size_t)b * T * 2048;
   cplx* psi_b = p.psi + (size_t)b * (T + 1) * m * n;
 
-  for (int i = tid; i < (NPB + NXB) * T_::MAT; i += G) Pb[i] = make_double2(0.0, 0.0);
+  for (int i = tid; i < (NPBUF + NXB) * T_::MAT; i += G) Pb[i] = make_double2(0.0, 0.0);
   __syncthreads();
   for (int idx = tid; idx < nn; idx += G) {
     const int r = idx / n, c = idx - r * n;
@@ -289,11 +294,17 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
 
   auto prefetch = [&](int t) {
     if (t < T) {
-      const cplx* src = Pg + (size_t)t * nn;
-      cplx* dst = Pb + (t % NPB) * T_::MAT;
-      for (int idx = tid; idx < nn; idx += G) {
-        const int r = idx / n, c = idx - r * n;
-        cp_async16(dst + swz<NP>(r, c), src + idx);
+      if (PF32) {
+        const float* src = Pgf + (size_t)t * 2048;
+        float* dst = Pstage + (t % NPB) * 2048;
+        for (int c = tid; c < 512; c += G) cp_async16(dst + 4 * c, src + 4 * c);
+      } else {
+        const cplx* src = Pg + (size_t)t * nn;
+        cplx* dst = Pb + (t % NPB) * T_::MAT;
+        for (int idx = tid; idx < nn; idx += G) {
+          const int r = idx / n, c = idx - r * n;
+          cp_async16(dst + swz<NP>(r, c), src + idx);
+        }
       }
     }
     cp_async_commit();
@@ -327,8 +338,16 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
     cplx* Xn = Xb + (NXB == 2 ? ((t + 1) & 1) : 0) * T_::MAT;
     if (t > 0) extract(Xc, t);
     prefetch(t + NPB - 1);
+    if (PF32) {                                       // widen the raw fp32 tile into the swizzled operand buffer
+      const float* src = Pstage + (t % NPB) * 2048;
+      for (int idx = tid; idx < nn; idx += G) {
+        const int r = idx / n, c = idx - r * n;
+        Pb[swz<NP>(r, c)] = make_double2((double)src[r * 32 + c], (double)src[1024 + r * 32 + c]);
+      }
+      __syncthreads();
+    }
     double cr[RB][CB][2], ci[RB][CB][2];
-    mma_gemm<NP, RB, CB>(Pb + (t % NPB) * T_::MAT, Xc, cr, ci, rb0, cb0, ksteps, lane);
+    mma_gemm<NP, RB, CB>(Pb + (PF32 ? 0 : (t % NPB)) * T_::MAT, Xc, cr, ci, rb0, cb0, ksteps, lane);
     if (NXB == 1) __syncthreads();                    // in-place update: every warp has finished reading X
     store_tile<NP, RB, CB>(Xn, cr, ci, rb0, cb0, lane);
   }
@@ -378,13 +397,14 @@ cudaError_t launch_expm(const QocParams& p, int sm_count, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int NP, int RB, int CB, int NPB, int NXB>
+template <int NP, int RB, int CB, int NPB, int NXB, bool PF32 = false>
 cudaError_t launch_chain(const QocParams& p, cudaStream_t st) {
   typedef MT<NP, RB, CB> T_;
-  const size_t smem = (size_t)(NPB + NXB) * T_::MAT * sizeof(cplx);
-  cudaError_t e = cudaFuncSetAttribute(k_chain_mma<NP, RB, CB, NPB, NXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = PF32 ? (size_t)(1 + NXB) * T_::MAT * sizeof(cplx) + (size_t)NPB * 2048 * sizeof(float)
+                           : (size_t)(NPB + NXB) * T_::MAT * sizeof(cplx);
+  cudaError_t e = cudaFuncSetAttribute(k_chain_mma<NP, RB, CB, NPB, NXB, PF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_chain_mma<NP, RB, CB, NPB, NXB><<<p.B, T_::THREADS, smem, st>>>(p);
+  k_chain_mma<NP, RB, CB, NPB, NXB, PF32><<<p.B, T_::THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -405,8 +425,17 @@ cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaSt
   return cudaErrorInvalidValue;
 }
 
-cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, cudaStream_t st, int64_t* launches) {
+cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaStream_t st, int64_t* launches) {
   ++*launches;
+  if (p_is_f32) {                                     // tcgen05 path: n <= 32
+    switch (NP) {
+      case 8: return launch_chain<8, 1, 1, 3, 2, true>(p, st);
+      case 16: return launch_chain<16, 1, 1, 3, 2, true>(p, st);
+      case 24: return launch_chain<24, 1, 1, 3, 2, true>(p, st);
+      case 32: return launch_chain<32, 1, 2, 3, 2, true>(p, st);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (NP) {
     case 8: return launch_chain<8, 1, 1, 3, 2>(p, st);
     case 16: return launch_chain<16, 1, 1, 3, 2>(p, st);

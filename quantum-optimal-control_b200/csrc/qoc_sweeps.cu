@@ -122,18 +122,29 @@ __global__ void k_fwd_reduce(QocParams p) {
 // ---------------------------------------------------------------------------------------------
 // k_costate: one CTA per instance, reverse sweep.  PT = storage type of P (double2 | float2).
 // ---------------------------------------------------------------------------------------------
+// PT = double2: interleaved [n][n] complex (fp64 path).  PT = float: planar padded [2][32][32] fp32
+// (tcgen05 path, csrc/qoc_tc_tf32.cu).
 template <typename PT>
-DEVINL cplx load_p(const PT* s, int i);
+struct PLay;
 template <>
-DEVINL cplx load_p<double2>(const double2* s, int i) { return s[i]; }
+struct PLay<double2> {
+  DEVINL static int item_elems(int n) { return n * n; }
+  DEVINL static cplx load(const double2* s, int r, int i, int n) { return s[r * n + i]; }
+};
 template <>
-DEVINL cplx load_p<float2>(const float2* s, int i) { const float2 v = s[i]; return make_double2((double)v.x, (double)v.y); }
+struct PLay<float> {
+  DEVINL static int item_elems(int) { return 2 * 32 * 32; }
+  DEVINL static cplx load(const float* s, int r, int i, int) {
+    return make_double2((double)s[r * 32 + i], (double)s[1024 + r * 32 + i]);
+  }
+};
 
 template <typename PT>
 __global__ void k_costate(QocParams p, int parts, int nbuf, int mc) {
   // grid = (B, ceil(m/mc)): the m costate columns are independent chains, a CTA sweeps mc of them
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = p.n, m = p.m, T = p.T, nn = n * n, mn = m * n;
+  const int n = p.n, m = p.m, T = p.T, mn = m * n;
+  const int nn = PLay<PT>::item_elems(n);        // elements of PT per cached propagator
   const int j0 = blockIdx.y * mc;
   const int mloc = min(mc, m - j0);
   const int ln = mloc * n;                                                       // local outputs
@@ -203,7 +214,7 @@ __global__ void k_costate(QocParams p, int parts, int nbuf, int mc) {
       const int j = idx / n, i = idx - j * n;
       const int r0 = q * rchunk, r1 = min(n, r0 + rchunk);
       cplx acc = make_double2(0.0, 0.0);
-      for (int r = r0; r < r1; ++r) cfma_conj(acc, load_p<PT>(Pt, r * n + i), lam_s[j * n + r]);
+      for (int r = r0; r < r1; ++r) cfma_conj(acc, PLay<PT>::load(Pt, r, i, n), lam_s[j * n + r]);
       part_s[w] = acc;
     }
     __syncthreads();
@@ -325,8 +336,8 @@ cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* 
 
 cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches) {
   ++*launches;
-  const int nn = p.n * p.n;
-  const size_t psz = p_is_f32 ? sizeof(float2) : sizeof(cplx);
+  const int nn = p_is_f32 ? 2 * 32 * 32 : p.n * p.n;
+  const size_t psz = p_is_f32 ? sizeof(float) : sizeof(cplx);
   // columns per CTA: all m when small, else chunks of <= 8 columns (more CTAs, less shared memory)
   int mc = p.m;
   if ((size_t)mc * p.n > 512) mc = 512 / p.n > 0 ? 512 / p.n : 1;
@@ -343,9 +354,9 @@ cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st
   const dim3 grid(p.B, (p.m + mc - 1) / mc);
   cudaError_t e;
   if (p_is_f32) {
-    e = cudaFuncSetAttribute(k_costate<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(k_costate<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_costate<float2><<<grid, threads, smem, st>>>(p, parts, nbuf, mc);
+    k_costate<float><<<grid, threads, smem, st>>>(p, parts, nbuf, mc);
   } else {
     e = cudaFuncSetAttribute(k_costate<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

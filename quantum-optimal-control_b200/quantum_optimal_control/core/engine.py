@@ -18,7 +18,7 @@ _DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF
 SYMBOLS = ["qoc_abi_version", "qoc_create", "qoc_destroy", "qoc_last_error", "qoc_workspace_bytes",
            "qoc_set_workspace", "qoc_set_problem", "qoc_set_regularizers", "qoc_value_and_grad", "qoc_evolve",
            "qoc_value_and_grad_host", "qoc_evolve_host", "qoc_debug_propagators", "qoc_launch_count", "qoc_set_profiling",
-           "qoc_kernel_times_ms"]
+           "qoc_kernel_times_ms", "qoc_poll_error"]
 
 
 class QocDims(C.Structure):
@@ -69,6 +69,7 @@ def load_library(path=None):
     lib.qoc_debug_propagators.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int)]
     lib.qoc_launch_count.argtypes = [vp]
     lib.qoc_launch_count.restype = C.c_int64
+    lib.qoc_poll_error.argtypes = [vp, vp]
     lib.qoc_set_profiling.argtypes = [vp, C.c_int]
     lib.qoc_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
     for fn in SYMBOLS:
@@ -248,16 +249,21 @@ class GrapeEngine:
         return dict(U_final=hU.numpy().copy(), inter_vecs=None if hiv is None else hiv.numpy().copy(),
                     loss=ho.numpy()[0].copy(), unitary_scale=ho.numpy()[1].copy())
 
+    def poll_error(self):
+        """Synchronise and raise if a device-side pipeline flagged a failure (tcgen05 path)."""
+        self._check(self.lib.qoc_poll_error(self._h, self._stream()))
+
     def propagators(self):
-        """Debug view of the cached propagators P[B,T,n,n] of the last call (clone)."""
+        """Debug view of the cached propagators of the last call as complex128 [B,T,n,n] (clone)."""
         t = self.torch
         ptr, eb = C.c_void_p(), C.c_int()
         self._check(self.lib.qoc_debug_propagators(self._h, C.byref(ptr), C.byref(eb)))
         off = ptr.value - self._ws.data_ptr()
-        nel = self.B * self.T * self.n * self.n
-        raw = self._ws[off:off + nel * eb.value]
-        dt = t.complex128 if eb.value == 16 else t.complex64
-        return raw.view(dt).reshape(self.B, self.T, self.n, self.n).clone()
+        if self.dims.dtype == QOC_F64:
+            nel = self.B * self.T * self.n * self.n
+            return self._ws[off:off + nel * 16].view(t.complex128).reshape(self.B, self.T, self.n, self.n).clone()
+        raw = self._ws[off:off + self.B * self.T * 2048 * 4].view(t.float32).reshape(self.B, self.T, 2, 32, 32)
+        return t.complex(raw[:, :, 0, :self.n, :self.n].double(), raw[:, :, 1, :self.n, :self.n].double())
 
     KERNELS = ("expm", "chain", "fwd_reduce", "costate", "grad", "finalize")
 

@@ -141,6 +141,7 @@ class run_session:
         uks = np.asarray(sp.ops_max_amp)[None, :, None] * w             # Get_uks
         Uf = ev['U_final'].cpu().numpy()
         self.inter_vecs = None if ev['inter_vecs'] is None else ev['inter_vecs'].cpu().numpy()
+        self.engine.poll_error()
         if sp.batched:
             self.uks, self.Uf = uks, Uf
         else:

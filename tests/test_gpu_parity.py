@@ -182,3 +182,38 @@ def test_cuda_matches_reference_goldens(name, built_lib):
     assert np.linalg.norm(Uf - g['U_final']) < 1e-8
     g32 = np.load(_os.path.join(_GOLD, "ref_%s_float32.npz" % name))    # the reference's real dtype
     assert np.linalg.norm(Uf - g32['U_final']) < 2e-3
+
+
+# ---- fp32-class tcgen05 path (QOC_TF32X3) -------------------------------------------------------------
+def _engine_tf32(args, kw, guess):
+    from quantum_optimal_control.core.problem import SystemParameters
+    from quantum_optimal_control.core.engine import GrapeEngine
+    H0, Hops, Hn, U, tt, steps, scl = args
+    sp = SystemParameters(H0, Hops, Hn, U, kw.get('U0', np.identity(len(H0))), tt, steps, scl, None, kw['maxA'], None, guess,
+                          False, kw.get('unitary_error', 1e-4), False, False, kw.get('reg_coeffs'), False, None,
+                          kw.get('Taylor_terms'), True, True, False, False, False)
+    return sp, GrapeEngine.from_sys_para(sp, dtype='tf32x3')
+
+
+@pytest.mark.parametrize("name", ['c1', 'c2_T40', 'c2_regs', 'c5_n16', 'c5_n8', 'c5_n20'])
+def test_tf32x3_tcgen05_path_matches_oracle(name, built_lib):
+    """Propagators from the tcgen05 kernel (3xTF32, fp32 accumulate in TMEM) vs the fp64 oracle.
+    Tolerances are fp32-class: |dP| < 2e-6 per propagator, ||dU_final||_F < 1e-4 * sqrt(T/40),
+    gradient 5e-4 relative to its scale (the reference itself computes in float32)."""
+    fn, over, B = CASES[name]
+    setups, guess, args, kw = make_case(fn(), seed=11, B=B, **over)
+    sp, eng = _engine_tf32(args, kw, guess)
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    out = eng.value_and_grad(base)
+    ev = eng.evolve(base)
+    eng.poll_error()
+    P = eng.propagators().cpu().numpy()
+    for b in range(B):
+        ref = O.costate_value_and_grad(setups[b], setups[b].ops_weight_base)
+        assert np.abs(P[b] - ref['P']).max() < 2e-6
+        T = setups[b].steps
+        assert np.linalg.norm(ev['U_final'][b].cpu().numpy() - ref['U_final']) < 1e-4 * max(1.0, np.sqrt(T / 40.0))
+        assert abs(out['loss'][b].item() - ref['loss']) < 1e-4
+        g = out['grad'][b].cpu().numpy()
+        assert np.abs(g - ref['grad']).max() < 5e-4 * max(np.abs(ref['grad']).max(), 1e-30)
+    eng.close()
