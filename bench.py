@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default: the config's)")
     ap.add_argument("--steps-T", type=int, default=None, help="override the number of time steps (debug only)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "tf32x3"], help="arithmetic of the propagator stage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -197,7 +198,7 @@ def run_ours(args):
         sp = SystemParameters(H0, Hops, Hn, U, np.identity(n), tt, steps, scl, None, kw['maxA'], None, guess, False,
                               kw.get('unitary_error', 1e-4), False, False, kw.get('reg_coeffs'), False, None,
                               kw.get('Taylor_terms'), True, True, False, False, False)
-    eng = GrapeEngine.from_sys_para(sp, device=dev)
+    eng = GrapeEngine.from_sys_para(sp, device=dev, dtype=args.dtype)
     p, s = sp.exp_terms, sp.scaling
     base0 = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).to(dev)
 
@@ -267,8 +268,12 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (k_expm) ----------------------------------------------
     peak, peak_src = None, None
     if rank == 0:
-        a = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
-        bb = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
+        tf32 = args.dtype == "tf32x3"
+        N, tdt = (8192, torch.float32) if tf32 else (4096, torch.float64)
+        old_flag = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        a = torch.randn(N, N, device=dev, dtype=tdt)
+        bb = torch.randn(N, N, device=dev, dtype=tdt)
         for _ in range(2):
             a @ bb
         best = 1e9
@@ -276,16 +281,27 @@ def run_ours(args):
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record(); a @ bb; s1.record(); torch.cuda.synchronize()
             best = min(best, s0.elapsed_time(s1))
-        peak = 2 * 4096 ** 3 / best / 1e9
-        peak_src = "cuBLAS DGEMM 4096^3 via torch.matmul, best of 5, measured in this run (MEASURED_PEAKS.json has no fp64 entry)"
+        torch.backends.cuda.matmul.allow_tf32 = old_flag
+        peak = 2 * N ** 3 / best / 1e9
+        peak_src = ("cuBLAS %s %d^3 via torch.matmul, best of 5, measured in this run (MEASURED_PEAKS.json has no %s entry)"
+                    % ("TF32 GEMM" if tf32 else "DGEMM", N, "tf32" if tf32 else "fp64"))
         del a, bb
     expm_ms = ktimes['expm'] / args.steps
     expm_flops = 8.0 * n ** 3 * (p - 1 + s) * T * B                    # (p-1) Taylor products + s squarings per (b,t)
     achieved = expm_flops / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else None
     step_flops = flops_alg(n, T, m, K, p, s) * B
-    roof = {"kernel": "k_expm", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+    ps_products = (1 + p // 2 - (1 if p % 2 == 0 else 0)) if p >= 2 else 0          # Paterson-Stockmeyer product count
+    np_pad = 32 if args.dtype == "tf32x3" else (n + 7) // 8 * 8
+    executed = 8.0 * np_pad ** 3 * (ps_products + s) * T * B * (3 if args.dtype == "tf32x3" else 1)
+    roof = {"kernel": "k_expm_tc32 (tcgen05)" if args.dtype == "tf32x3" else "k_expm_mma (DMMA)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
-            "peak_source": peak_src, "pipe": "fp64 (tcgen05 has no f64 kind; bound is the FP64 FMA/DMMA pipe)",
+            "peak_source": peak_src,
+            "pipe": ("tf32 tensor pipe via tcgen05 (3 MMAs per product: 3xTF32 operand split)" if args.dtype == "tf32x3"
+                     else "fp64 (tcgen05 has no f64 kind; bound is the FP64 FMA/DMMA pipe)"),
+            "executed_flops_per_launch": executed,
+            "executed_frac_of_peak": (executed / (expm_ms * 1e-3) / 1e12 / peak) if (expm_ms > 0 and peak) else None,
+            "note": "achieved uses SURVEY 8(d)'s algorithmic count (p-1+s products of 8n^3); executed counts the "
+                    "Paterson-Stockmeyer products actually issued on the padded tile (and the 3x split for tf32x3)",
             "alg_flops_per_launch": expm_flops, "avg_launch_ms": expm_ms,
             "kernel_ms_per_step": {k: v / args.steps for k, v in ktimes.items()},
             "whole_step_alg_tflops": step_flops / (ms_per_step * 1e-3) / 1e12}
@@ -300,9 +316,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: n=%d K=%d T=%d m=%d B=%d per GPU, (p,s)=(%d,%d), fp64" % (
-                args.workload, n, K, T, m, B, p, s), "batch_iterations_per_s": args.steps / (ms_max * 1e-3),
+            "dtype": "f64" if args.dtype == "f64" else "tf32x3 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "%s: n=%d K=%d T=%d m=%d B=%d per GPU, (p,s)=(%d,%d), %s" % (
+                args.workload, n, K, T, m, B, p, s, args.dtype), "batch_iterations_per_s": args.steps / (ms_max * 1e-3),
                 "l2": "inputs exceed L2: %.2f GB of propagators are rewritten and re-read every step" % (
                     B * T * n * n * 16 / 1e9), "final_loss_min": final_loss},
             "clocks": clk.summary(),
