@@ -91,10 +91,15 @@ DEVINL uint32_t b_off(int n, int k) {
 
 // write this thread's stacked row rho (rho < 32: Re row rho, else Im row rho-32) of a matrix into the
 // embedded A-form [[Xr,-Xi],[Xi,Xr]] (hi and lo) and / or the B-form [Xr; Xi]^T.
+DEVINL void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+DEVINL void sts32(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+
 template <bool WA, bool WB>
-DEVINL void write_operands(unsigned char* sA_hi, unsigned char* sB_hi, int rho, const float (&v)[32]) {
-  unsigned char* sA_lo = sA_hi + A_BYTES;
-  unsigned char* sB_lo = sB_hi + B_BYTES;
+DEVINL void write_operands(uint32_t sA_hi, uint32_t sB_hi, int rho, const float (&v)[32]) {
+  const uint32_t sA_lo = sA_hi + A_BYTES;
+  const uint32_t sB_lo = sB_hi + B_BYTES;
   const int row2 = rho < 32 ? rho + 32 : rho - 32;
   const float sgn = rho < 32 ? 1.0f : -1.0f;
 #pragma unroll
@@ -104,17 +109,17 @@ DEVINL void write_operands(unsigned char* sA_hi, unsigned char* sB_hi, int rho, 
     for (int e = 0; e < 4; ++e) split_tf32(v[4 * cc + e], hi[e], lo[e]);
     if (WA) {
       const uint32_t o1 = a_off(rho, 0, cc), o2 = a_off(row2, 1, cc);
-      *reinterpret_cast<float4*>(sA_hi + o1) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(sA_lo + o1) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<float4*>(sA_hi + o2) = make_float4(sgn * hi[0], sgn * hi[1], sgn * hi[2], sgn * hi[3]);
-      *reinterpret_cast<float4*>(sA_lo + o2) = make_float4(sgn * lo[0], sgn * lo[1], sgn * lo[2], sgn * lo[3]);
+      sts128(sA_hi + o1, hi[0], hi[1], hi[2], hi[3]);
+      sts128(sA_lo + o1, lo[0], lo[1], lo[2], lo[3]);
+      sts128(sA_hi + o2, sgn * hi[0], sgn * hi[1], sgn * hi[2], sgn * hi[3]);
+      sts128(sA_lo + o2, sgn * lo[0], sgn * lo[1], sgn * lo[2], sgn * lo[3]);
     }
     if (WB) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const uint32_t o = b_off(4 * cc + e, rho);
-        *reinterpret_cast<float*>(sB_hi + o) = hi[e];
-        *reinterpret_cast<float*>(sB_lo + o) = lo[e];
+        sts32(sB_hi + o, hi[e]);
+        sts32(sB_lo + o, lo[e]);
       }
     }
   }
@@ -129,9 +134,9 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int it = lane >> 4;                      // which item of the pair this thread serves
   const int rho = 16 * warp + (lane & 15);       // stacked accumulator row
-  unsigned char* sA = smem + it * ITEM_BYTES;    // A_hi | A_lo | B_hi | B_lo
-  unsigned char* sB = sA + 2 * A_BYTES;
-  float* stg = reinterpret_cast<float*>(sB);     // H staging [64][33] aliases the B-form region
+  const uint32_t sA = smem_u32(smem) + it * ITEM_BYTES;    // A_hi | A_lo | B_hi | B_lo (shared-window addresses)
+  const uint32_t sB = sA + 2 * A_BYTES;
+  const float* stg = reinterpret_cast<const float*>(smem + it * ITEM_BYTES + 2 * A_BYTES);   // H staging [64][33] aliases the B-form region
   const int n = p.n, K = p.K, T = p.T;
   const long long items = (long long)p.B * T;
   const long long pairs = (items + 1) >> 1;
@@ -156,12 +161,19 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0) {
+    if (warp == 0) {
+     // every value below is warp-uniform, so the descriptors live in uniform registers and the
+     // elected lane issues back-to-back UTCHMMAs without a divergence "waterfall"
+     const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+     const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
+     uint32_t elected;
+     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
+     if (elected) {
       for (int i = 0; i < nvalid; ++i) {
-        const uint32_t base = smem_u32(smem + i * ITEM_BYTES);
+        const uint32_t base = sbase + i * ITEM_BYTES;
         const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + A_BYTES);
         const uint64_t b_hi = make_desc(base + 2 * A_BYTES), b_lo = make_desc(base + 2 * A_BYTES + B_BYTES);
-        const uint32_t d = taddr + ((uint32_t)(16 * i) << 16);
+        const uint32_t d = tbase + ((uint32_t)(16 * i) << 16);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t ao = (uint64_t)((ks & 3) * 2 + (ks >> 2) * (8192 >> 4));
@@ -172,6 +184,8 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
         }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+     }
+     __syncwarp();
     }
     const long long t_start = clock64();
     bool timed_out = false;
