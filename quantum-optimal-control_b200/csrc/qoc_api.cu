@@ -13,9 +13,9 @@ static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 static int pick_np(int n) { return n <= 64 ? (n + 7) / 8 * 8 : -1; }
 
-struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, total; };
+struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, scratch, total; };
 
-static WsLayout ws_layout(const qoc_dims_t& d) {
+static WsLayout ws_layout(const qoc_dims_t& d, int sm_count) {
   WsLayout L;
   const size_t nn = (size_t)d.n * d.n, mn = (size_t)d.m * d.n;
   // propagators: fp64 interleaved [n][n] complex, or (QOC_TF32X3) fp32 planar padded [2][32][32]
@@ -31,6 +31,8 @@ static WsLayout ws_layout(const qoc_dims_t& d) {
   L.st_base = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_grad = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_out = off; off += align_up((size_t)d.B * 4 * sizeof(double));
+  L.scratch = off;
+  if (d.n > 64) off += align_up(qoc_large_scratch_elems(d.n, d.B, sm_count) * sizeof(cplx));
   L.total = off;
   return L;
 }
@@ -72,10 +74,7 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
     h->err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
     return QOC_ECUDA;
   }
-  if (d.dtype == QOC_F64 && h->NP < 0) {
-    h->err = "QOC_F64 supports n <= 64";
-    return QOC_EINVAL;
-  }
+  if (d.n > 64 && d.n > 1024) { h->err = "n too large"; return QOC_EINVAL; }
   if (d.dtype == QOC_TF32X3 && (d.n > 32 || d.K > 15)) {
     h->err = "QOC_TF32X3 (tcgen05 path) supports n <= 32, K <= 15 in this build";
     return QOC_EINVAL;
@@ -101,13 +100,13 @@ const char* qoc_last_error(qoc_handle_t h) { return h ? h->err.c_str() : "null h
 int qoc_workspace_bytes(qoc_handle_t h, size_t* bytes) {
   QOC_CHECK_H(h);
   if (!bytes) return QOC_EINVAL;
-  *bytes = ws_layout(h->d).total;
+  *bytes = ws_layout(h->d, h->sm_count).total;
   return QOC_OK;
 }
 
 int qoc_set_workspace(qoc_handle_t h, void* dev_ptr, size_t bytes) {
   QOC_CHECK_H(h);
-  const WsLayout L = ws_layout(h->d);
+  const WsLayout L = ws_layout(h->d, h->sm_count);
   if (!dev_ptr || ((uintptr_t)dev_ptr & 255)) { h->err = "workspace must be 256-byte aligned"; return QOC_EINVAL; }
   if (bytes < L.total) { h->err = "workspace too small"; return QOC_ENOMEM; }
   char* w = (char*)dev_ptr;
@@ -117,6 +116,7 @@ int qoc_set_workspace(qoc_handle_t h, void* dev_ptr, size_t bytes) {
   h->gctrl = (double*)(w + L.gctrl); h->ot = (cplx*)(w + L.ot); h->scal = (double*)(w + L.scal);
   h->Ufin = (cplx*)(w + L.Ufin);
   h->st_base = (double*)(w + L.st_base); h->st_grad = (double*)(w + L.st_grad); h->st_out = (double*)(w + L.st_out);
+  h->scratch = w + L.scratch;
   h->ws_set = true;
   return QOC_OK;
 }
@@ -252,10 +252,13 @@ static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   int rc;
   h->ev_recorded = 0;
   if ((rc = prof_mark(h, 0, st))) return rc;
+  const bool large = h->d.n > 64;                   // matrices do not fit in shared memory: tiled global-operand path
   if (h->d.dtype == QOC_TF32X3) CUDA_TRY(h, qoc_launch_expm_tc32(p, h->sm_count, h->err_flag, st, &h->launches));
+  else if (large) CUDA_TRY(h, qoc_launch_expm_large(p, h->sm_count, h->scratch, st, &h->launches));
   else CUDA_TRY(h, qoc_launch_expm_f64(p, h->NP, h->sm_count, st, &h->launches));
   if ((rc = prof_mark(h, 1, st))) return rc;
-  CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, h->d.dtype != QOC_F64, st, &h->launches));
+  if (large) CUDA_TRY(h, qoc_launch_chain_large(p, h->scratch, st, &h->launches));
+  else CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, h->d.dtype != QOC_F64, st, &h->launches));
   if ((rc = prof_mark(h, 2, st))) return rc;
   CUDA_TRY(h, qoc_launch_fwd_reduce(p, st, &h->launches));
   if ((rc = prof_mark(h, 3, st))) return rc;
@@ -274,7 +277,8 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
   cudaStream_t st = (cudaStream_t)stream;
   rc = run_forward(h, p, st);
   if (rc) return rc;
-  CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
+  if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, st, &h->launches));
+  else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
   if ((rc = prof_mark(h, 4, st))) return rc;
   CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, st, &h->launches));
   if ((rc = prof_mark(h, 5, st))) return rc;

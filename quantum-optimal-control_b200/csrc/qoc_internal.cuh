@@ -65,6 +65,7 @@ struct qoc_handle_s {
   char* ws; size_t ws_bytes;
   void* P; cplx *psi, *lam, *ot, *Ufin; double *gctrl, *scal;
   double *st_base, *st_grad, *st_out;     // staging for the *_host entry points
+  void* scratch;                          // n > 64: per-CTA global intermediates
   int64_t launches;
   bool profiling; int ev_recorded;
   cudaEvent_t ev[QOC_NUM_KERNELS + 1];
@@ -74,6 +75,10 @@ struct qoc_handle_s {
 cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_expm_tc32(const QocParams& p, int sm_count, int* err_flag, cudaStream_t st, int64_t* launches);
+size_t qoc_large_scratch_elems(int n, int B, int sm_count);
+cudaError_t qoc_launch_expm_large(const QocParams& p, int sm_count, void* scratch, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_chain_large(const QocParams& p, void* scratch, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_costate_large(const QocParams& p, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_grad(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches);

@@ -33,6 +33,10 @@ CASES = {
     'c5_n48': (lambda: W.c5_random(48, T=6), {}, 1),
     'c5_n50': (lambda: W.c5_random(50, T=5), {}, 1),
     'c5_n64': (lambda: W.c5_random(64, T=5), {}, 1),
+    'c5_n72': (lambda: W.c5_random(72, T=3), {}, 1),
+    'c5_n100_regs': (lambda: W.c5_random(100, T=3), dict(states_concerned_list=[0, 5, 99], reg_coeffs={'dwdt': 0.1, 'forbidden_coeff_list': [2.0], 'states_forbidden_list': [7]}), 2),
+    'c5_n128': (lambda: W.c5_random(128, T=2), dict(states_concerned_list=list(range(8))), 1),
+    'c4_T4': (lambda: W.c4_three_transmon_toffoli(T=4), dict(total_time=0.2), 1),
     'n5_U0': (lambda: W.c5_random(5, T=15), dict(U0=np.linalg.qr(np.random.default_rng(5).normal(size=(5, 5)) +
                                                                   1j * np.random.default_rng(6).normal(size=(5, 5)))[0],
                                                   states_concerned_list=[1, 3]), 2),
