@@ -60,7 +60,12 @@ enum {
 };
 
 /* qoc_dims_t.flags */
-#define QOC_FLAG_NO_FULL_CHAIN 1u   /* skip the n x n chain (U_final / unitary_scale not produced; psi only) */
+/* state-transfer mode (core/tensorflow_state.py:77-142,244-261,331-335): per-step propagator is the
+ * Taylor sum of order exp_terms-1 WITHOUT scaling/squaring, unitary_scale is
+ * (sum_j |psi_j(T)|^2)^2 / m^2, V / phi are arbitrary state vectors (pass concerned_idx = NULL).
+ * The reverse sweep uses Q_t^dagger, which equals the reference's sum_j (-H)^j/j! for Hermitian
+ * Hamiltonians (the host layer checks that). */
+#define QOC_FLAG_STATE_TRANSFER 1u
 
 typedef struct qoc_handle_s* qoc_handle_t;
 

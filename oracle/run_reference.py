@@ -189,6 +189,7 @@ def golden_cases():
         'c2_small_allregs': (c2r, 8, conv(8)),
         'c3_small_forbidden': (c3s, 9, conv(6)),
         'c5_n16': (W.c5_random(16, T=20), 10, conv(5)),
+        'state_transfer_n8': (W.state_transfer_random(8, T=20, m=2), 11, conv(6)),
     }
 
 

@@ -45,7 +45,7 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   if (!out || !dims) return QOC_EINVAL;
   *out = nullptr;
   const qoc_dims_t& d = *dims;
-  if (d.n < 1 || d.K < 0 || d.K > 31 || d.T < 1 || d.m < 1 || d.B < 1 || d.exp_terms < 1 || d.exp_terms > 31 || d.scaling < 0 ||
+  if (d.n < 1 || d.K < 0 || d.K > 31 || d.T < 1 || d.m < 1 || d.B < 1 || d.exp_terms < 1 || d.exp_terms > 31 || ((d.flags & QOC_FLAG_STATE_TRANSFER) && d.exp_terms < 2) || d.scaling < 0 ||
       d.scaling > 60)
     return QOC_EINVAL;
   if (d.dtype != QOC_F64 && d.dtype != QOC_TF32X3) return QOC_EINVAL;
@@ -226,8 +226,10 @@ static int fill_params(qoc_handle_t h, QocParams& p, const double* base) {
   const qoc_dims_t& d = h->d;
   std::memset(&p, 0, sizeof(p));
   p.n = d.n; p.K = d.K; p.T = d.T; p.m = d.m; p.B = d.B; p.p = d.exp_terms; p.s = d.scaling;
+  p.state_transfer = (d.flags & QOC_FLAG_STATE_TRANSFER) ? 1 : 0;
+  if (p.state_transfer) { p.p = d.exp_terms - 1; p.s = 0; }      // order p-1, no squaring (tensorflow_state.py:92)
   p.has_cidx = h->has_cidx;
-  p.dt = h->dt; p.inv2s = 1.0 / (double)(1ull << d.scaling);
+  p.dt = h->dt; p.inv2s = 1.0 / (double)(1ull << p.s);
   { double f = 1.0; p.invfact[0] = 1.0; for (int j = 1; j < 32; ++j) { f *= (double)j; p.invfact[j] = 1.0 / f; } }
   p.A = h->A; p.U0 = h->U0; p.phi = h->phi; p.V = h->V; p.cidx = h->cidx; p.maxA = h->maxA;
   p.env = h->env; p.fw = h->fw;

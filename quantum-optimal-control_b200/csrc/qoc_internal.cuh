@@ -11,6 +11,7 @@ typedef double2 cplx;
 struct QocParams {
   int n, K, T, m, B, p, s;
   int has_cidx;
+  int state_transfer;
   double dt, inv2s;
   double invfact[32];   // 1/j!
   // constants

@@ -77,6 +77,7 @@ __global__ void k_fwd_reduce(QocParams p) {
   const bool forb = p.reg.has_forbidden && p.fw != nullptr;
   const bool spd = p.reg.has_speed_up != 0;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};       // o.re o.im forb S
+  double nrm = 0.0;                           // state transfer: sum_j |psi_j(T)|^2
   const int t_lo = (forb || spd) ? 0 : T;
   for (int t = t_lo + w; t <= T; t += nw) {
     const cplx* ps = psi_b + (size_t)t * mn;
@@ -93,6 +94,7 @@ __global__ void k_fwd_reduce(QocParams p) {
         const double pop = x.x * x.x + x.y * x.y;
         f += p.fw[idx % n] * pop * pop;
       }
+      if (p.state_transfer && t == T) nrm += x.x * x.x + x.y * x.y;
     }
     orr = warp_sum(orr); oi = warp_sum(oi);
     acc[2] += f;
@@ -102,8 +104,11 @@ __global__ void k_fwd_reduce(QocParams p) {
     }
   }
   block_sum<4>(acc, red);
+  double nv[1] = {nrm};
+  if (p.state_transfer) block_sum<1>(nv, red);
   if (threadIdx.x == 0) {
     const double m2 = (double)m * (double)m;
+    if (p.state_transfer) p.scal[(size_t)b * 8 + 5] = nv[0] * nv[0] / m2;      // tensorflow_state.py:335
     const double loss = 1.0 - (acc[0] * acc[0] + acc[1] * acc[1]) / m2;
     double statereg = 0.0, spdfac = 0.0;
     if (forb) statereg += 0.5 * acc[2] / (double)T;                   // sum_f (c_f/T) * l2_loss(pop)

@@ -13,6 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__fi
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libqoc_b200.so")
 
 QOC_F64, QOC_TF32X3 = 0, 1
+QOC_FLAG_STATE_TRANSFER = 1
 _DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF32X3}
 
 SYMBOLS = ["qoc_abi_version", "qoc_create", "qoc_destroy", "qoc_last_error", "qoc_workspace_bytes",
@@ -283,13 +284,19 @@ class GrapeEngine:
     @classmethod
     def from_sys_para(cls, sp, B=None, dtype='f64', device=None):
         """Build an engine from a ``SystemParameters`` (unitary mode)."""
+        flags = 0
         if sp.state_transfer:
-            raise NotImplementedError("state_transfer=True is not implemented by the CUDA engine yet")
+            # the reverse sweep uses Q_t^dagger; the reference uses sum_j (-H)^j/j! (tensorflow_state.py:118-131),
+            # identical for Hermitian Hamiltonians only
+            for Hm in [sp.H0_c] + list(sp.ops_c):
+                if not np.allclose(Hm, np.conj(np.transpose(Hm)), rtol=0, atol=1e-12 * max(1.0, np.abs(Hm).max())):
+                    raise NotImplementedError("state_transfer=True needs Hermitian H0 / Hops in the CUDA engine")
+            flags |= QOC_FLAG_STATE_TRANSFER
         if sp.is_dressed and sp.reg_coeffs.get('forbid_dressed'):
             raise NotImplementedError("forbid_dressed is not implemented by the CUDA engine yet")
         B = sp.batch_size if B is None else B
         eng = cls(sp.state_num, sp.ops_len, sp.steps, len(sp.states_concerned_list), B, sp.exp_terms, sp.scaling,
-                  dtype=dtype, device=device)
+                  dtype=dtype, device=device, flags=flags)
         eng.set_problem(sp.A_c, sp.U0_c, sp.target_vectors_c, sp.V_c, sp.concerned_idx, sp.ops_max_amp, sp.dt)
         eng.set_regularizers(sp.reg_coeffs, sp.one_minus_gauss)
         return eng

@@ -24,6 +24,6 @@ def engine_for(problem_args, kw, guess):
     H0, Hops, Hn, U, tt, steps, scl = problem_args
     kw = dict(kw)
     sp = SystemParameters(H0, Hops, Hn, U, kw.get('U0', np.identity(len(H0))), tt, steps, scl, kw.get('dressed_info'),
-                          kw['maxA'], None, guess, False, kw.get('unitary_error', 1e-4), False, False,
+                          kw['maxA'], None, guess, False, kw.get('unitary_error', 1e-4), kw.get('state_transfer', False), False,
                           kw.get('reg_coeffs'), False, None, kw.get('Taylor_terms'), True, True, False, False, False)
     return sp, GrapeEngine.from_sys_para(sp)

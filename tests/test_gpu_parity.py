@@ -175,13 +175,18 @@ def test_cuda_matches_reference_goldens(name, built_lib):
     assert abs(out['unitary_scale'][0].item() - g['eval_unitary_scale']) < 1e-10
     assert np.abs(out['grad'][0].cpu().numpy() - g['eval_grad']).max() < 1e-9 * max(1.0, np.abs(g['eval_grad']).max())
     fs = g['eval_final_state']
-    assert np.linalg.norm(ev['U_final'][0].cpu().numpy() - (fs[:n, :n] + 1j * fs[n:, :n])) < 1e-9
+    st = bool(pb.get('state_transfer', False))
+    if not st:
+        assert np.linalg.norm(ev['U_final'][0].cpu().numpy() - (fs[:n, :n] + 1j * fs[n:, :n])) < 1e-9
     ivp = g['eval_inter_vecs_packed']                                   # [2n, T+1, m]
     iv = np.transpose(ivp[:n] + 1j * ivp[n:], (1, 2, 0))                 # [T+1, m, n]
     assert np.abs(ev['inter_vecs'][0].cpu().numpy() - iv).max() < 1e-9
     eng.close()
     uks, Uf = Grape(*args, convergence=conv, initial_guess=g['guess'], save=False, show_plots=False, quiet=True, **kw)
     assert np.abs(uks - g['uks']).max() < 1e-8
+    if st:
+        assert len(Uf) == 0
+        return
     assert np.linalg.norm(Uf - g['U_final']) < 1e-5        # north_star bar; observed ~1e-12
     assert np.linalg.norm(Uf - g['U_final']) < 1e-8
     g32 = np.load(_os.path.join(_GOLD, "ref_%s_float32.npz" % name))    # the reference's real dtype

@@ -38,7 +38,10 @@ def test_oracle_matches_reference_goldens_fp64(name):
     assert np.abs(np.transpose(out.inter_vecs, (1, 2, 0)) - g['eval_inter_vecs_packed']).max() < 1e-12
     uks, Uf = O.grape(*args, convergence=conv, initial_guess=g['guess'], **kw)
     assert np.abs(uks - g['uks']).max() < 1e-10
-    assert np.linalg.norm(Uf - g['U_final']) < 1e-10
+    if setup.state_transfer:
+        assert len(Uf) == 0 and g['U_final'].size == 0           # run_session.py:109-110
+    else:
+        assert np.linalg.norm(Uf - g['U_final']) < 1e-10
 
 
 @pytest.mark.parametrize("name", ['c1_pi_pulse', 'c2_small_allregs'])
@@ -58,6 +61,8 @@ def test_costate_form_equals_graph_form():
     for name in golden_cases():
         g = np.load(os.path.join(GOLD, "ref_%s_float64.npz" % name))
         setup, *_ = _setup(name, g['guess'])
+        if setup.state_transfer:
+            continue
         a = O.graph_value_and_grad(setup, setup.ops_weight_base)
         b = O.costate_value_and_grad(setup, setup.ops_weight_base)
         assert abs(a.loss - b['loss']) < 1e-12 and abs(a.reg_loss - b['reg_loss']) < 1e-11 * max(1, abs(a.reg_loss))

@@ -122,6 +122,21 @@ def c5_random(n, T=1000, K=2, seed=1234):
                 unitary_error=1e-4)
 
 
+def state_transfer_random(n=8, T=20, m=2, seed=77):
+    """State-transfer problem (reference: state_transfer=True): m random initial / target state vectors under
+    the C5-style random Hermitian Hamiltonian; ``states_concerned_list`` holds the initial vectors, ``U`` the targets."""
+    pb = c5_random(n, T=T)
+    rng = np.random.default_rng(seed)
+
+    def vec():
+        v = rng.normal(size=n) + 1j * rng.normal(size=n)
+        return v / np.linalg.norm(v)
+
+    pb.pop('Taylor_terms')
+    pb.update(states_concerned_list=[vec() for _ in range(m)], U=[vec() for _ in range(m)], state_transfer=True)
+    return pb
+
+
 WORKLOADS = {
     'C1': (c1_pi_pulse, dict(B=1)),
     'C2': (c2_transmon_cavity, dict(B=256)),
