@@ -1,6 +1,7 @@
 // C-ABI front end of libqoc_b200.so (declared in include/qoc_b200.h).
 #include "qoc_internal.cuh"
 #include <cstring>
+#include <cmath>
 #include <cstdio>
 #include <vector>
 #include <new>
@@ -161,6 +162,20 @@ int qoc_set_problem(qoc_handle_t h, const double* A_host, const double* U0_host,
     off[k + 1] = (int)rr.size();
   }
   h->nnz = (int)rr.size();
+  // anti-Hermitian generators (Hermitian Hamiltonians) enable the triangle-only Taylor evaluation
+  h->herm = 1;
+  for (int k = 0; k <= d.K && h->herm; ++k) {
+    const double* Ak = A_host + (size_t)k * nn * 2;
+    double amax = 0.0;
+    for (size_t i = 0; i < nn * 2; ++i) amax = fabs(Ak[i]) > amax ? fabs(Ak[i]) : amax;
+    const double tol = 1e-13 * (amax > 1.0 ? amax : 1.0);
+    for (int r = 0; r < d.n && h->herm; ++r)
+      for (int c = r; c < d.n; ++c) {
+        const double* x = Ak + ((size_t)r * d.n + c) * 2;
+        const double* y = Ak + ((size_t)c * d.n + r) * 2;
+        if (fabs(x[0] + y[0]) > tol || fabs(x[1] - y[1]) > tol) { h->herm = 0; break; }
+      }
+  }
   // union sparsity pattern of A_0..A_K with per-entry coefficient vectors, for the H assembly
   std::vector<int> prc;
   std::vector<double> pcf;
@@ -229,6 +244,7 @@ static int fill_params(qoc_handle_t h, QocParams& p, const double* base) {
   p.state_transfer = (d.flags & QOC_FLAG_STATE_TRANSFER) ? 1 : 0;
   if (p.state_transfer) { p.p = d.exp_terms - 1; p.s = 0; }      // order p-1, no squaring (tensorflow_state.py:92)
   p.has_cidx = h->has_cidx;
+  p.herm = h->herm;
   p.dt = h->dt; p.inv2s = 1.0 / (double)(1ull << p.s);
   { double f = 1.0; p.invfact[0] = 1.0; for (int j = 1; j < 32; ++j) { f *= (double)j; p.invfact[j] = 1.0 / f; } }
   p.A = h->A; p.U0 = h->U0; p.phi = h->phi; p.V = h->V; p.cidx = h->cidx; p.maxA = h->maxA;

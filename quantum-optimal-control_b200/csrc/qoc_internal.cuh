@@ -12,6 +12,7 @@ struct QocParams {
   int n, K, T, m, B, p, s;
   int has_cidx;
   int state_transfer;
+  int herm;             // every generator A_k is anti-Hermitian (Hermitian Hamiltonians)
   double dt, inv2s;
   double invfact[32];   // 1/j!
   // constants
@@ -59,7 +60,7 @@ struct qoc_handle_s {
   int *cidx, *coo_off, *coo_r, *coo_c, *pat_rc;
   int pat_n;
   double *maxA, *env, *fw;
-  int has_cidx, nnz;
+  int has_cidx, nnz, herm;
   double dt;
   qoc_reg_t reg;
   // workspace carve-up

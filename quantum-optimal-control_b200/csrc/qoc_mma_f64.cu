@@ -128,6 +128,142 @@ DEVINL void item_sync() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Hermitian-structure evaluation of the Taylor polynomial (used when every generator A_k is
+// anti-Hermitian, i.e. the Hamiltonians are Hermitian -- checked on the host):
+//   S = E(H2) + H O(H2),  H2 = H H,  E = sum_i c_{2i} H2^i,  O = sum_i c_{2i+1} H2^i.
+// H2, its powers, E and O are Hermitian and H O is anti-Hermitian, so every product only needs
+// its upper block triangle (NBLK(NBLK+1)/2 of NBLK^2 8x8 blocks); the lower triangle is written by
+// mirroring.  Warp W owns block rows W and NBLK-1-W, which balances the triangle exactly.
+// ---------------------------------------------------------------------------------------------
+template <int NP, int W>
+struct HT {
+  static constexpr int NBLK = NP / 8;
+  static constexpr int RA = W, RB_ = NBLK - 1 - W;
+  static constexpr int CA = NBLK - RA;       // blocks (RA, RA..NBLK-1)
+  static constexpr int CB_ = NBLK - RB_;     // blocks (RB_, RB_..NBLK-1)
+  static constexpr int NB = CA + CB_;        // = NBLK + 1
+};
+
+// upper-triangle product: acc[b] over this warp's blocks; b < CA -> (RA, RA+b), else (RB_, RB_+b-CA)
+template <int NP, int W>
+DEVINL void tri_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, double (&cr)[HT<NP, W>::NB][2],
+                     double (&ci)[HT<NP, W>::NB][2], int ksteps, int lane) {
+  typedef HT<NP, W> H_;
+  const int g = lane >> 2, q = lane & 3;
+  const int ra = 8 * H_::RA + g, rb = 8 * H_::RB_ + g;
+  const int ma = sw_mask(ra), mb = sw_mask(rb);
+#pragma unroll
+  for (int b = 0; b < H_::NB; ++b) cr[b][0] = cr[b][1] = ci[b][0] = ci[b][1] = 0.0;
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k = 4 * ks + q;
+    const cplx a0 = A[ra * NP + (k ^ ma)], a1 = A[rb * NP + (k ^ mb)];
+    const int bm = sw_mask(k);
+    const cplx* Brow = B + k * NP;
+    cplx bv[H_::CA];                           // columns RA..NBLK-1 (superset of RB_..NBLK-1)
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) bv[j] = Brow[(8 * (H_::RA + j) + g) ^ bm];
+    const double na0 = -a0.y, na1 = -a1.y;
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) dmma(cr[j][0], cr[j][1], a0.x, bv[j].x);
+#pragma unroll
+    for (int j = 0; j < H_::CB_; ++j) dmma(cr[H_::CA + j][0], cr[H_::CA + j][1], a1.x, bv[H_::RB_ - H_::RA + j].x);
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) dmma(ci[j][0], ci[j][1], a0.x, bv[j].y);
+#pragma unroll
+    for (int j = 0; j < H_::CB_; ++j) dmma(ci[H_::CA + j][0], ci[H_::CA + j][1], a1.x, bv[H_::RB_ - H_::RA + j].y);
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) dmma(cr[j][0], cr[j][1], na0, bv[j].y);
+#pragma unroll
+    for (int j = 0; j < H_::CB_; ++j) dmma(cr[H_::CA + j][0], cr[H_::CA + j][1], na1, bv[H_::RB_ - H_::RA + j].y);
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) dmma(ci[j][0], ci[j][1], a0.y, bv[j].x);
+#pragma unroll
+    for (int j = 0; j < H_::CB_; ++j) dmma(ci[H_::CA + j][0], ci[H_::CA + j][1], a1.y, bv[H_::RB_ - H_::RA + j].x);
+  }
+}
+
+// Store the warp's upper-triangle blocks of  U = X + Y  and mirror the strictly-upper blocks as
+// L[c][r] = conj(X[r][c]) * sx + conj(Y[r][c]) * sy  (sx/sy = +1 Hermitian part, -1 anti-Hermitian part).
+template <int NP, int W>
+DEVINL void tri_store(cplx* __restrict__ M, const double (&xr)[HT<NP, W>::NB][2], const double (&xi)[HT<NP, W>::NB][2],
+                      const double (&yr)[HT<NP, W>::NB][2], const double (&yi)[HT<NP, W>::NB][2], bool use_y, double sx,
+                      double sy, int lane) {
+  typedef HT<NP, W> H_;
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int b = 0; b < H_::NB; ++b) {
+    const int bi = b < H_::CA ? H_::RA : H_::RB_;
+    const int bj = b < H_::CA ? H_::RA + b : H_::RB_ + (b - H_::CA);
+    const int r = 8 * bi + g;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = 8 * bj + 2 * q + e;
+      const double ur = xr[b][e] + (use_y ? yr[b][e] : 0.0), ui = xi[b][e] + (use_y ? yi[b][e] : 0.0);
+      M[swz<NP>(r, c)] = make_double2(ur, ui);
+      if (bi != bj) {
+        const double lr = sx * xr[b][e] + (use_y ? sy * yr[b][e] : 0.0);
+        const double li = -(sx * xi[b][e] + (use_y ? sy * yi[b][e] : 0.0));
+        M[swz<NP>(c, r)] = make_double2(lr, li);
+      }
+    }
+  }
+}
+
+// Taylor phase for warp W; leaves the full S in buf1.  Needs p >= 2.
+template <int NP, int W, int WARPS>
+DEVINL void herm_taylor(const QocParams& p, const cplx* Hs, cplx* buf1, cplx* buf2, int n, int ksteps, int lane) {
+  typedef HT<NP, W> H_;
+  constexpr int NB = H_::NB;
+  const int g = lane >> 2, q = lane & 3;
+  const int pp = p.p;
+  auto coef = [&](int j) -> double { return j <= pp ? p.invfact[j] : 0.0; };
+  double ar[NB][2], ai[NB][2], er[NB][2], ei[NB][2], orr[NB][2], oi[NB][2];
+  tri_gemm<NP, W>(Hs, Hs, ar, ai, ksteps, lane);                  // H2
+  {
+    const double c0 = coef(0), c1 = coef(1), c2 = coef(2), c3 = coef(3);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int bi = b < H_::CA ? H_::RA : H_::RB_;
+      const int bj = b < H_::CA ? H_::RA + b : H_::RB_ + (b - H_::CA);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = 8 * bi + g, c = 8 * bj + 2 * q + e;
+        const double id = (r == c && r < n) ? 1.0 : 0.0;
+        er[b][e] = c0 * id + c2 * ar[b][e]; ei[b][e] = c2 * ai[b][e];
+        orr[b][e] = c1 * id + c3 * ar[b][e]; oi[b][e] = c3 * ai[b][e];
+      }
+    }
+  }
+  tri_store<NP, W>(buf1, ar, ai, ar, ai, false, 1.0, 1.0, lane);  // H2 (Hermitian), full
+  item_sync<WARPS>();
+  const int imax = pp / 2;                                         // highest power of H2 needed
+  for (int i = 2; i <= imax; ++i) {
+    tri_gemm<NP, W>(buf1, i == 2 ? buf1 : buf2, ar, ai, ksteps, lane);      // H2^i
+    const double ce = coef(2 * i), co = coef(2 * i + 1);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        er[b][e] += ce * ar[b][e]; ei[b][e] += ce * ai[b][e];
+        orr[b][e] += co * ar[b][e]; oi[b][e] += co * ai[b][e];
+      }
+    if (i < imax) {
+      item_sync<WARPS>();                                          // everyone has finished reading buf2
+      tri_store<NP, W>(buf2, ar, ai, ar, ai, false, 1.0, 1.0, lane);
+      item_sync<WARPS>();
+    }
+  }
+  item_sync<WARPS>();
+  tri_store<NP, W>(buf2, orr, oi, orr, oi, false, 1.0, 1.0, lane);   // O (Hermitian), full
+  item_sync<WARPS>();
+  tri_gemm<NP, W>(Hs, buf2, ar, ai, ksteps, lane);                  // A = H O  (anti-Hermitian)
+  // S = E + A above the diagonal, conj(E) - conj(A) = (E - A)^H below; buf1 (H2) is no longer read
+  tri_store<NP, W>(buf1, er, ei, ar, ai, true, 1.0, -1.0, lane);
+  item_sync<WARPS>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_expm_mma: persistent over (b,t) items.  An item is owned by WARPS warps; when WARPS == 1 a
 // CTA carries 4 independent items (one per warp), else exactly one.  Shared memory per item:
 // H, ping, pong (3 x NP^2 x 16 B) + 32 weights.
@@ -183,6 +319,36 @@ k_expm_mma(QocParams p) {
     // Paterson-Stockmeyer form with block size 2: S = (..(B_r H2 + B_{r-1}) H2 + ..) H2 + B_0,
     // B_i = c_{2i} I + c_{2i+1} H, c_j = 1/j!  -> 1 + floor(p/2) - [p even] products instead of p-1.
     double sr[RB][CB][2], si[RB][CB][2];
+    // Hermitian Hamiltonians (all generators anti-Hermitian): triangle-only products, see herm_taylor
+    constexpr bool HERM_OK = (NP == 32 && RB == 2 && CB == 4) || (NP == 16 && RB == 2 && CB == 2);
+    const bool use_herm = HERM_OK && p.herm && p.p >= 2;
+    if (HERM_OK && use_herm) {
+      if (NP == 32) {
+        if (warp == 0) herm_taylor<NP, 0, WARPS>(p, Hs, buf1, buf2, n, ksteps, lane);
+        else herm_taylor<NP, (NP == 32 ? 1 : 0), WARPS>(p, Hs, buf1, buf2, n, ksteps, lane);
+      } else {
+        herm_taylor<NP, 0, WARPS>(p, Hs, buf1, buf2, n, ksteps, lane);
+      }
+      // S is complete in buf1: squarings read it directly, or it is copied out when s == 0
+      cplx* X = buf1;
+      cplx* Y = buf2;
+      if (p.s == 0) {
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int j = 0; j < CB; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const cplx v = X[swz<NP>(8 * (rb0 + i) + g, 8 * (cb0 + j) + 2 * q + e)];
+              sr[i][j][e] = v.x; si[i][j][e] = v.y;
+            }
+      }
+      for (int s = 0; s < p.s; ++s) {
+        if (s > 0) { store_tile<NP, RB, CB>(X, sr, si, rb0, cb0, lane); item_sync<WARPS>(); }
+        mma_gemm<NP, RB, CB>(X, X, sr, si, rb0, cb0, ksteps, lane);
+        cplx* tmp = X; X = Y; Y = tmp;
+      }
+    } else {
     auto add_block = [&](double c_id, double c_h, bool init) {     // S (+)= c_id*I + c_h*H on this lane's fragments
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
@@ -244,6 +410,7 @@ k_expm_mma(QocParams p) {
         cplx* tmp = X; X = Y; Y = tmp;
       }
     }
+    }  // general (non-Hermitian) path
     cplx* dst = Pout + (size_t)item * nn;
 #pragma unroll
     for (int i = 0; i < RB; ++i) {

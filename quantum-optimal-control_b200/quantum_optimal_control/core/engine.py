@@ -224,10 +224,19 @@ class GrapeEngine:
             self._pinned[key] = t.empty(tuple(shape), dtype=td).pin_memory()
         return self._pinned[key]
 
-    def value_and_grad_host(self, base_np):
-        """NumPy in, NumPy out; H2D + kernels + D2H inside the call (pinned staging buffers)."""
+    def host_buffers(self):
+        """Pinned host arrays (NumPy views) a caller may fill / read directly to avoid extra copies:
+        dict(base[B,K,T], grad[B,K,T])."""
+        return dict(base=self._pin('base', (self.B, self.K, self.T)).numpy(),
+                    grad=self._pin('grad', (self.B, self.K, self.T)).numpy())
+
+    def value_and_grad_host(self, base_np, copy=True):
+        """NumPy in, NumPy out; H2D + kernels + D2H inside the call (pinned staging buffers).
+        ``base_np`` may be the pinned ``host_buffers()['base']`` itself; with ``copy=False`` the returned
+        arrays are views of the pinned result buffers (valid until the next call)."""
         hb = self._pin('base', (self.B, self.K, self.T))
-        hb.numpy()[...] = np.asarray(base_np, dtype=np.float64).reshape(self.B, self.K, self.T)
+        if base_np is not hb.numpy():
+            hb.numpy()[...] = np.asarray(base_np, dtype=np.float64).reshape(self.B, self.K, self.T)
         hg = self._pin('grad', (self.B, self.K, self.T))
         ho = self._pin('out', (4, self.B))
         p = lambda x: C.c_void_p(x.data_ptr())
@@ -235,6 +244,8 @@ class GrapeEngine:
             self._check(self.lib.qoc_value_and_grad_host(
                 self._h, p(hb), p(ho[0]), p(ho[1]), p(hg), p(ho[2]), p(ho[3]), self._stream()))
         o = ho.numpy()
+        if not copy:
+            return dict(loss=o[0], reg_loss=o[1], grad=hg.numpy(), unitary_scale=o[2], grad_squared=o[3])
         return dict(loss=o[0].copy(), reg_loss=o[1].copy(), grad=hg.numpy().copy(), unitary_scale=o[2].copy(),
                     grad_squared=o[3].copy())
 

@@ -50,11 +50,25 @@ class TF1AdamHost:
         self.b1, self.b2, self.eps = beta1, beta2, eps
 
     def step(self, theta, grad, lr):
+        """In-place update of ``theta`` (returned for convenience); no temporaries beyond one scratch array."""
         self.t += 1
         lr_t = lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
-        self.m = self.b1 * self.m + (1.0 - self.b1) * grad
-        self.v = self.b2 * self.v + (1.0 - self.b2) * grad * grad
-        return theta - lr_t * self.m / (np.sqrt(self.v) + self.eps)
+        if getattr(self, '_tmp', None) is None or self._tmp.shape != grad.shape:
+            self._tmp = np.empty_like(self.m)
+        tmp = self._tmp
+        self.m *= self.b1
+        np.multiply(grad, 1.0 - self.b1, out=tmp)
+        self.m += tmp
+        self.v *= self.b2
+        np.multiply(grad, grad, out=tmp)
+        tmp *= (1.0 - self.b2)
+        self.v += tmp
+        np.sqrt(self.v, out=tmp)
+        tmp += self.eps
+        np.divide(self.m, tmp, out=tmp)
+        tmp *= lr_t
+        theta -= tmp
+        return theta
 
 
 class run_session:

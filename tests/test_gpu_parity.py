@@ -231,3 +231,33 @@ def test_tf32x3_tcgen05_path_matches_oracle(name, built_lib):
         g = out['grad'][b].cpu().numpy()
         assert np.abs(g - ref['grad']).max() < 3e-3 * max(np.abs(ref['grad']).max(), 1e-30)
     eng.close()
+
+
+# ---- degenerate shapes ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", ["T1", "K1_m1", "B5_odd"])
+def test_edge_shapes(shape, built_lib):
+    """T = 1 (no costate step), a single control / single concerned state, odd batch sizes."""
+    if shape == "T1":
+        pb, B = dict(W.c5_random(6, T=1), reg_coeffs={'dwdt': 0.5, 'd2wdt2': 0.1, 'amplitude': 0.2}), 2
+    elif shape == "K1_m1":
+        pb, B = dict(W.c5_random(7, T=9, K=1), states_concerned_list=[3]), 1
+    else:
+        pb, B = dict(W.c2_transmon_cavity(T=6), total_time=12.0), 5
+    setups, guess, args, kw = make_case(pb, seed=31, B=B)
+    for dtype in ('f64', 'tf32x3'):
+        if dtype == 'f64':
+            sp, eng = engine_for(args, kw, guess)
+        else:
+            sp, eng = _engine_tf32(args, kw, guess)
+        base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+        out = eng.value_and_grad(base)
+        ev = eng.evolve(base)
+        eng.poll_error()
+        tol = 1e-9 if dtype == 'f64' else 2e-3
+        for b in range(B):
+            ref = O.graph_value_and_grad(setups[b], setups[b].ops_weight_base)
+            assert abs(out['loss'][b].item() - ref.loss) < tol
+            assert abs(out['reg_loss'][b].item() - ref.reg_loss) < tol * max(1.0, abs(ref.reg_loss))
+            assert np.abs(out['grad'][b].cpu().numpy() - ref.grad).max() < tol * max(np.abs(ref.grad).max(), 1e-30) + (0 if dtype == 'f64' else 1e-7)
+            assert np.linalg.norm(ev['U_final'][b].cpu().numpy() - O.r_to_c_mat(ref.final_state, setups[b].n)) < tol
+        eng.close()
