@@ -347,7 +347,7 @@ cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st
   int mc = p.m;
   if ((size_t)mc * p.n > 512) mc = 512 / p.n > 0 ? 512 / p.n : 1;
   const int ln = mc * p.n;
-  const int threads = ln >= 256 ? 256 : 128;
+  const int threads = 256;
   int parts = threads / ln;
   if (parts < 1) parts = 1;
   if (parts > 8) parts = 8;
