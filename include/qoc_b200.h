@@ -120,6 +120,11 @@ int qoc_set_problem(qoc_handle_t h, const double* A_host, const double* U0_host,
 int qoc_set_regularizers(qoc_handle_t h, const qoc_reg_t* reg, const double* envelope_host,
                          const double* forbid_weight_host, void* stream);
 
+/* forbid_dressed (core/regularization_functions.py:73-80): evaluate the forbidden-state populations on
+ * psi' = W psi with W_host [n][n] complex = v_sorted^dagger (host pointer, copied); NULL switches it off.
+ * Allocates one internal device buffer of B*(T+1)*m*n complex for the transformed states. */
+int qoc_set_forbid_basis(qoc_handle_t h, const double* W_host, void* stream);
+
 /* One fwd+bwd evaluation for all B instances (== B calls of run_session.get_error).
  *   base_dev          [B][K][T]  ops_weight_base (controls are maxA_k * sin(base))
  *   loss_dev          [B]        1 - |sum_j <phi_j|psi_j(T)>|^2 / m^2

@@ -60,6 +60,7 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   h->cidx = h->coo_off = h->coo_r = h->coo_c = h->pat_rc = nullptr;
   h->pat_n = 0;
   h->maxA = h->env = h->fw = nullptr;
+  h->dressW = h->psid = nullptr;
   h->has_cidx = 0; h->nnz = 0; h->dt = 0.0;
   std::memset(&h->reg, 0, sizeof(h->reg));
   h->ws = nullptr; h->ws_bytes = 0;
@@ -90,7 +91,7 @@ int qoc_destroy(qoc_handle_t h) {
   QOC_CHECK_H(h);
   cudaFree(h->A); cudaFree(h->U0); cudaFree(h->phi); cudaFree(h->V); cudaFree(h->coo_v);
   cudaFree(h->cidx); cudaFree(h->coo_off); cudaFree(h->coo_r); cudaFree(h->coo_c);
-  cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw); cudaFree(h->pat_rc); cudaFree(h->pat_coef); cudaFree(h->pat_coef_f); cudaFree(h->err_flag);
+  cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw); cudaFree(h->dressW); cudaFree(h->psid); cudaFree(h->pat_rc); cudaFree(h->pat_coef); cudaFree(h->pat_coef_f); cudaFree(h->err_flag);
   for (int i = 0; i <= QOC_NUM_KERNELS; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return QOC_OK;
@@ -234,6 +235,17 @@ int qoc_set_regularizers(qoc_handle_t h, const qoc_reg_t* reg, const double* env
   return QOC_OK;
 }
 
+extern "C" int qoc_set_forbid_basis(qoc_handle_t h, const double* W_host, void* stream) {
+  QOC_CHECK_H(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!W_host) { cudaFree(h->dressW); h->dressW = nullptr; return QOC_OK; }
+  const qoc_dims_t& d = h->d;
+  CUDA_TRY(h, upload(&h->dressW, W_host, (size_t)d.n * d.n, st));
+  if (!h->psid) CUDA_TRY(h, cudaMalloc((void**)&h->psid, (size_t)d.B * (d.T + 1) * d.m * d.n * sizeof(cplx)));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QOC_OK;
+}
+
 static int fill_params(qoc_handle_t h, QocParams& p, const double* base) {
   if (!h->ws_set) { h->err = "qoc_set_workspace not called"; return QOC_ESTATE; }
   if (!h->problem_set) { h->err = "qoc_set_problem not called"; return QOC_ESTATE; }
@@ -249,6 +261,7 @@ static int fill_params(qoc_handle_t h, QocParams& p, const double* base) {
   { double f = 1.0; p.invfact[0] = 1.0; for (int j = 1; j < 32; ++j) { f *= (double)j; p.invfact[j] = 1.0 / f; } }
   p.A = h->A; p.U0 = h->U0; p.phi = h->phi; p.V = h->V; p.cidx = h->cidx; p.maxA = h->maxA;
   p.env = h->env; p.fw = h->fw;
+  p.dressW = (h->reg.has_forbidden && h->fw) ? h->dressW : nullptr; p.psid = h->psid;
   p.coo_off = h->coo_off; p.coo_r = h->coo_r; p.coo_c = h->coo_c; p.coo_v = h->coo_v;
   p.pat_n = h->pat_n; p.pat_rc = h->pat_rc; p.pat_coef = h->pat_coef; p.pat_coef_f = h->pat_coef_f;
   p.reg = h->reg;
@@ -278,6 +291,7 @@ static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   if (large) CUDA_TRY(h, qoc_launch_chain_large(p, h->scratch, st, &h->launches));
   else CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, h->d.dtype != QOC_F64, st, &h->launches));
   if ((rc = prof_mark(h, 2, st))) return rc;
+  if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 0, st, &h->launches));
   CUDA_TRY(h, qoc_launch_fwd_reduce(p, st, &h->launches));
   if ((rc = prof_mark(h, 3, st))) return rc;
   return QOC_OK;
@@ -295,6 +309,7 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
   cudaStream_t st = (cudaStream_t)stream;
   rc = run_forward(h, p, st);
   if (rc) return rc;
+  if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 1, st, &h->launches));
   if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, st, &h->launches));
   else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
   if ((rc = prof_mark(h, 4, st))) return rc;

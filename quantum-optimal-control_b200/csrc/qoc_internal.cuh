@@ -24,6 +24,8 @@ struct QocParams {
   const double* maxA;   // [K]
   const double* env;    // [K][T] or null
   const double* fw;     // [n] or null   (forbidden weights, not yet /T)
+  const cplx* dressW;   // [n][n] or null: forbidden populations taken on W psi (forbid_dressed)
+  cplx* psid;           // [B][T+1][m][n]: W psi, then (in place) the dressed costate sources
   const int* coo_off;   // [K+1]
   const int* coo_r;     // [nnz]
   const int* coo_c;     // [nnz]
@@ -60,6 +62,7 @@ struct qoc_handle_s {
   int *cidx, *coo_off, *coo_r, *coo_c, *pat_rc;
   int pat_n;
   double *maxA, *env, *fw;
+  cplx *dressW, *psid;
   int has_cidx, nnz, herm;
   double dt;
   qoc_reg_t reg;
@@ -81,6 +84,7 @@ size_t qoc_large_scratch_elems(int n, int B, int sm_count);
 cudaError_t qoc_launch_expm_large(const QocParams& p, int sm_count, void* scratch, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_chain_large(const QocParams& p, void* scratch, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate_large(const QocParams& p, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_dress(const QocParams& p, int phase, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_grad(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches);

@@ -297,7 +297,10 @@ __global__ void k_costate_large(QocParams p, int mc) {
   const double m2 = (double)m * (double)m;
   auto source = [&](int t, int idx) -> cplx {
     cplx s = make_double2(0.0, 0.0);
-    if (forb) {
+    if (forb && p.dressW) {
+      const cplx d = p.psid[((size_t)b * (T + 1) + t) * mn + (size_t)j0 * n + idx];
+      s.x += d.x; s.y += d.y;
+    } else if (forb) {
       const cplx x = psi_b[(size_t)t * mn + idx];
       const double pop = x.x * x.x + x.y * x.y;
       const double c = p.fw[idx % n] / (double)T * 2.0 * pop;

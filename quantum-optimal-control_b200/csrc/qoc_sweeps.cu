@@ -66,6 +66,45 @@ template <int N>
 DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ---------------------------------------------------------------------------------------------
+// k_dress: forbid_dressed support, a warp per (b, t, j) state vector.
+//   phase 0: psid = W psi                                  (regularization_functions.py:79)
+//   phase 1: psid <- W^dagger ( (fw/T) * 2 |psid|^2 psid )  = the costate source of the dressed term
+// ---------------------------------------------------------------------------------------------
+__global__ void k_dress(QocParams p, int phase) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = p.n, m = p.m, T = p.T;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  cplx* vec = reinterpret_cast<cplx*>(smem_raw) + (size_t)wib * n;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long items = (long long)p.B * (T + 1) * m;
+  for (long long item = warp; item < items; item += nwarps) {
+    const cplx* src = (phase == 0 ? p.psi : p.psid) + (size_t)item * n;
+    cplx* dst = p.psid + (size_t)item * n;
+    for (int c = lane; c < n; c += 32) {
+      cplx x = src[c];
+      if (phase == 1) {
+        const double pop = x.x * x.x + x.y * x.y;
+        const double f = p.fw[c] / (double)T * 2.0 * pop;
+        x.x *= f; x.y *= f;
+      }
+      vec[c] = x;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      double ax = 0.0, ay = 0.0;
+      for (int c = 0; c < n; ++c) {
+        const cplx v = vec[c];
+        if (phase == 0) { const cplx w = p.dressW[(size_t)i * n + c]; ax += w.x * v.x - w.y * v.y; ay += w.x * v.y + w.y * v.x; }
+        else { const cplx w = p.dressW[(size_t)c * n + i]; ax += w.x * v.x + w.y * v.y; ay += w.x * v.y - w.y * v.x; }
+      }
+      dst[i] = make_double2(ax, ay);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_fwd_reduce: one CTA per instance; a warp per time step.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_fwd_reduce(QocParams p) {
@@ -73,6 +112,7 @@ __global__ void k_fwd_reduce(QocParams p) {
   const int b = blockIdx.x, n = p.n, m = p.m, T = p.T;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const cplx* psi_b = p.psi + (size_t)b * (T + 1) * m * n;
+  const cplx* psif_b = (p.dressW ? p.psid : p.psi) + (size_t)b * (T + 1) * m * n;   // states the forbidden term looks at
   const int mn = m * n;
   const bool forb = p.reg.has_forbidden && p.fw != nullptr;
   const bool spd = p.reg.has_speed_up != 0;
@@ -91,7 +131,8 @@ __global__ void k_fwd_reduce(QocParams p) {
         oi += ph.x * x.y - ph.y * x.x;
       }
       if (forb) {
-        const double pop = x.x * x.x + x.y * x.y;
+        const cplx y = p.dressW ? psif_b[(size_t)t * mn + idx] : x;
+        const double pop = y.x * y.x + y.y * y.y;
         f += p.fw[idx % n] * pop * pop;
       }
       if (p.state_transfer && t == T) nrm += x.x * x.x + x.y * x.y;
@@ -171,7 +212,10 @@ __global__ void k_costate(QocParams p, int parts, int nbuf, int mc) {
 
   auto source = [&](int t, int idx) -> cplx {          // regulariser source at time t for local element idx=(jl,i)
     cplx s = make_double2(0.0, 0.0);
-    if (forb) {
+    if (forb && p.dressW) {
+      const cplx d = p.psid[((size_t)b * (T + 1) + t) * mn + (size_t)j0 * n + idx];     // precomputed by k_dress phase 1
+      s.x += d.x; s.y += d.y;
+    } else if (forb) {
       const cplx x = psi_b[(size_t)t * mn + idx];
       const double pop = x.x * x.x + x.y * x.y;
       const double c = p.fw[idx % n] / (double)T * 2.0 * pop;
@@ -333,6 +377,18 @@ __global__ void k_finalize(QocParams p) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+cudaError_t qoc_launch_dress(const QocParams& p, int phase, cudaStream_t st, int64_t* launches) {
+  ++*launches;
+  const long long items = (long long)p.B * (p.T + 1) * p.m;
+  long long blocks = (items + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const size_t smem = (size_t)8 * p.n * sizeof(cplx);
+  cudaError_t e = cudaFuncSetAttribute(k_dress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_dress<<<(unsigned)blocks, 256, smem, st>>>(p, phase);
+  return cudaGetLastError();
+}
+
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches) {
   ++*launches;
   k_fwd_reduce<<<p.B, 256, 0, st>>>(p);

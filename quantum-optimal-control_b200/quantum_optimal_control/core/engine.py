@@ -19,7 +19,7 @@ _DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF
 SYMBOLS = ["qoc_abi_version", "qoc_create", "qoc_destroy", "qoc_last_error", "qoc_workspace_bytes",
            "qoc_set_workspace", "qoc_set_problem", "qoc_set_regularizers", "qoc_value_and_grad", "qoc_evolve",
            "qoc_value_and_grad_host", "qoc_evolve_host", "qoc_debug_propagators", "qoc_launch_count", "qoc_set_profiling",
-           "qoc_kernel_times_ms", "qoc_poll_error"]
+           "qoc_kernel_times_ms", "qoc_poll_error", "qoc_set_forbid_basis"]
 
 
 class QocDims(C.Structure):
@@ -71,6 +71,7 @@ def load_library(path=None):
     lib.qoc_launch_count.argtypes = [vp]
     lib.qoc_launch_count.restype = C.c_int64
     lib.qoc_poll_error.argtypes = [vp, vp]
+    lib.qoc_set_forbid_basis.argtypes = [vp, dp, vp]
     lib.qoc_set_profiling.argtypes = [vp, C.c_int]
     lib.qoc_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
     for fn in SYMBOLS:
@@ -179,6 +180,12 @@ class GrapeEngine:
             assert env.shape == (self.K, self.T)
         with self.torch.cuda.device(self.device):
             self._check(self.lib.qoc_set_regularizers(self._h, C.byref(r), _np_ptr(env), _np_ptr(fw), self._stream()))
+
+    def set_forbid_basis(self, W):
+        """forbid_dressed: forbidden populations are taken on W @ psi (W = v_sorted^dagger); None switches it off."""
+        Wc = None if W is None else np.ascontiguousarray(W, dtype=np.complex128)
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.qoc_set_forbid_basis(self._h, _np_ptr(Wc), self._stream()))
 
     # ------------------------------------------------------------------------------------------
     def _base(self, base):
@@ -303,11 +310,12 @@ class GrapeEngine:
                 if not np.allclose(Hm, np.conj(np.transpose(Hm)), rtol=0, atol=1e-12 * max(1.0, np.abs(Hm).max())):
                     raise NotImplementedError("state_transfer=True needs Hermitian H0 / Hops in the CUDA engine")
             flags |= QOC_FLAG_STATE_TRANSFER
-        if sp.is_dressed and sp.reg_coeffs.get('forbid_dressed'):
-            raise NotImplementedError("forbid_dressed is not implemented by the CUDA engine yet")
         B = sp.batch_size if B is None else B
         eng = cls(sp.state_num, sp.ops_len, sp.steps, len(sp.states_concerned_list), B, sp.exp_terms, sp.scaling,
                   dtype=dtype, device=device, flags=flags)
         eng.set_problem(sp.A_c, sp.U0_c, sp.target_vectors_c, sp.V_c, sp.concerned_idx, sp.ops_max_amp, sp.dt)
         eng.set_regularizers(sp.reg_coeffs, sp.one_minus_gauss)
+        if sp.is_dressed and sp.reg_coeffs.get('forbid_dressed') and 'forbidden_coeff_list' in sp.reg_coeffs:
+            from ..helper_functions.grape_functions import sort_ev      # regularization_functions.py:73-80
+            eng.set_forbid_basis(np.conj(np.transpose(sort_ev(sp.v_c, sp.dressed_id))))
         return eng

@@ -261,3 +261,55 @@ def test_edge_shapes(shape, built_lib):
             assert np.abs(out['grad'][b].cpu().numpy() - ref.grad).max() < tol * max(np.abs(ref.grad).max(), 1e-30) + (0 if dtype == 'f64' else 1e-7)
             assert np.linalg.norm(ev['U_final'][b].cpu().numpy() - O.r_to_c_mat(ref.final_state, setups[b].n)) < tol
         eng.close()
+
+
+# ---- SciPy driver and dressed basis -----------------------------------------------------------------------
+def test_lbfgs_driver_matches_scipy_on_oracle(built_lib):
+    """method='L-BFGS-B' (core/run_session.py:151-196): the same scipy.optimize.minimize call driven by the
+    CPU oracle's get_error must land on the same pulse."""
+    from scipy.optimize import minimize
+    from quantum_optimal_control.main_grape.grape import Grape
+    pb = W.c1_pi_pulse(T=30)
+    args, kw = W.grape_kwargs(pb)
+    guess = W.random_guess(2, 30, pb['maxA'], 17)
+    conv = {'rate': 0.01, 'update_step': 10, 'max_iterations': 12, 'conv_target': 1e-12, 'learning_rate_decay': 100}
+    uks, Uf = Grape(*args, convergence=conv, initial_guess=guess, method='L-BFGS-B', save=False, show_plots=False,
+                    quiet=True, **kw)
+    H0, Hops, Hn, U, tt, steps, scl = args
+    st = O.make_setup(H0, Hops, U, tt, steps, scl, initial_guess=guess, **kw)
+
+    def fun(x):
+        o = O.graph_value_and_grad(st, x.reshape(2, 30))
+        return np.float64(o.reg_loss), np.float64(o.grad.reshape(-1))
+
+    res = minimize(fun, np.asarray(st.ops_weight_base).reshape(-1), method='L-BFGS-B', jac=True,
+                   options={'maxfun': 12, 'gtol': 1e-25, 'disp': False, 'maxls': 40})
+    ref_uks = np.asarray(pb['maxA'])[:, None] * np.sin(res['x'].reshape(2, 30))
+    assert np.abs(uks - ref_uks).max() < 1e-6
+    assert O.graph_value_and_grad(st, res['x'].reshape(2, 30)).loss < O.graph_value_and_grad(st, st.ops_weight_base).loss
+
+
+@pytest.mark.parametrize("forbid_dressed", [False, True])
+def test_dressed_initial_vectors(forbid_dressed, built_lib):
+    """dressed_info: initial vectors are eigenvectors of H0 (core/system_parameters.py:178-179) -> general-V path."""
+    from quantum_optimal_control.helper_functions.grape_functions import get_dressed_info
+    pb = dict(W.c2_transmon_cavity(T=12), total_time=24.0)
+    H0d = pb['H0'] + 0.05 * (pb['Hops'][0] + pb['Hops'][2])           # make the dressed basis non-trivial
+    w_c, v_c, ids = get_dressed_info(H0d)
+    pb['H0'] = H0d
+    pb['dressed_info'] = {'eigenvectors': v_c, 'dressed_id': ids, 'eigenvalues': w_c, 'is_dressed': True}
+    pb['reg_coeffs'] = {'forbidden_coeff_list': [2.0, 1.0], 'states_forbidden_list': [20, 11], 'forbid_dressed': forbid_dressed}
+    setups, guess, args, kw = make_case(pb, seed=41, B=2)
+    sp, eng = engine_for(args, kw, guess)
+    assert sp.concerned_idx is None
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    out = eng.value_and_grad(base)
+    ev = eng.evolve(base)
+    for b in range(2):
+        ref = O.graph_value_and_grad(setups[b], setups[b].ops_weight_base)
+        n = setups[b].n
+        assert abs(out['loss'][b].item() - ref.loss) < 1e-10 and abs(out['reg_loss'][b].item() - ref.reg_loss) < 1e-10
+        assert np.abs(out['grad'][b].cpu().numpy() - ref.grad).max() < 1e-9 * np.abs(ref.grad).max()
+        iv_ref = np.transpose(ref.inter_vecs[:, :n, :] + 1j * ref.inter_vecs[:, n:, :], (2, 0, 1))
+        assert np.abs(ev['inter_vecs'][b].cpu().numpy() - iv_ref).max() < 1e-9
+    eng.close()
