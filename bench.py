@@ -54,6 +54,8 @@ def make_problem(name, T=None):
     if T is not None:
         full = fn()
         pb['total_time'] = full['total_time'] * T / full['steps']      # same dt
+        if 'Taylor_terms' not in pb:
+            pass
     return pb, dict(meta)
 
 

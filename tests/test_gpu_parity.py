@@ -313,3 +313,33 @@ def test_dressed_initial_vectors(forbid_dressed, built_lib):
         iv_ref = np.transpose(ref.inter_vecs[:, :n, :] + 1j * ref.inter_vecs[:, n:, :], (2, 0, 1))
         assert np.abs(ev['inter_vecs'][b].cpu().numpy() - iv_ref).max() < 1e-9
     eng.close()
+
+
+def test_full_size_c3_properties(built_lib):
+    """BASELINE config C3 at full size (n=36, T=1000, B=1024, forbidden-state regulariser on 27 states):
+    instance 0 and 1023 against the oracle, batch-permutation equivariance, loss consistent with U_final."""
+    pb = W.c3_two_transmon_cnot()
+    B = 1024
+    setups, _, args, kw = make_case(pb, seed=500, B=1)
+    guess = W.random_guess(4, 1000, pb['maxA'], 500, B=B)
+    sp, eng = engine_for(args, kw, guess)
+    assert (sp.exp_terms, sp.scaling) == (8, 2)
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    out = {k: v.clone() for k, v in eng.value_and_grad(base).items()}
+    U = eng.evolve(base, want_inter_vecs=False)['U_final']
+    phi = torch.from_numpy(sp.target_vectors_c).cuda()
+    idx = torch.as_tensor(sp.concerned_idx, device='cuda', dtype=torch.long)
+    o = (phi.conj()[None] * U[:, :, idx].transpose(1, 2)).sum(dim=(1, 2))
+    assert ((1 - (o.abs() ** 2) / 16) - out['loss']).abs().max().item() < 1e-10
+    assert (out['reg_loss'] >= out['loss']).all()
+    perm = torch.randperm(B, device='cuda')
+    outp = eng.value_and_grad(base[perm].contiguous())
+    assert torch.equal(outp['grad'], out['grad'][perm]) and torch.equal(outp['reg_loss'], out['reg_loss'][perm])
+    for b in (0, B - 1):
+        H0, Hops, Hn, Ut, tt, steps, scl = args
+        st = O.make_setup(H0, Hops, Ut, tt, steps, scl, initial_guess=guess[b], **kw)
+        ref = O.graph_value_and_grad(st, st.ops_weight_base)
+        assert np.linalg.norm(U[b].cpu().numpy() - O.r_to_c_mat(ref.final_state, 36)) < 1e-8
+        assert abs(out['reg_loss'][b].item() - ref.reg_loss) < 1e-9
+        assert np.abs(out['grad'][b].cpu().numpy() - ref.grad).max() < 1e-9 * np.abs(ref.grad).max()
+    eng.close()

@@ -142,6 +142,12 @@ WORKLOADS = {
     'C2': (c2_transmon_cavity, dict(B=256)),
     'C3': (c3_two_transmon_cnot, dict(B=1024)),
     'C4': (c4_three_transmon_toffoli, dict(B=128)),
+    # C5 is the 8-GPU sweep over n with 4096 instances in total = 512 per GPU
+    'C5n8': (lambda T=1000: c5_random(8, T=T), dict(B=512)),
+    'C5n16': (lambda T=1000: c5_random(16, T=T), dict(B=512)),
+    'C5n32': (lambda T=1000: c5_random(32, T=T), dict(B=512)),
+    'C5n64': (lambda T=1000: c5_random(64, T=T), dict(B=512)),
+    'C5n128': (lambda T=1000: c5_random(128, T=T), dict(B=512)),
 }
 
 
