@@ -153,6 +153,11 @@ int qoc_evolve_host(qoc_handle_t h, const double* base_host, double* U_final_hos
  * propagators P[B][T][n][n] (complex double for QOC_F64, complex float for QOC_TF32X3). */
 int qoc_debug_propagators(qoc_handle_t h, void** P_dev, int* elem_bytes);
 
+/* Instances processed per pass.  When the workspace for all B instances would exceed the memory budget
+ * (80 % of free device memory at qoc_create, or QOC_B200_MAX_WS_GB), the batch is processed in chunks that
+ * reuse the same workspace; results are identical, qoc_workspace_bytes reports the reduced size. */
+int qoc_batch_chunk(qoc_handle_t h);
+
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t qoc_launch_count(qoc_handle_t h);
 

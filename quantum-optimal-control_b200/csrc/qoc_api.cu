@@ -2,6 +2,7 @@
 #include "qoc_internal.cuh"
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <vector>
 #include <new>
@@ -16,24 +17,25 @@ static int pick_np(int n) { return n <= 64 ? (n + 7) / 8 * 8 : -1; }
 
 struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, scratch, total; };
 
-static WsLayout ws_layout(const qoc_dims_t& d, int sm_count) {
+static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
+  // Bc = instances processed per pass (batch chunk); P / psi / lam / gctrl / ot / scratch are reused by every pass
   WsLayout L;
   const size_t nn = (size_t)d.n * d.n, mn = (size_t)d.m * d.n;
   // propagators: fp64 interleaved [n][n] complex, or (QOC_TF32X3) fp32 planar padded [2][32][32]
   const size_t p_item = d.dtype == QOC_F64 ? nn * sizeof(cplx) : (size_t)2 * 32 * 32 * sizeof(float);
   size_t off = 0;
-  L.P = off; off += align_up((size_t)d.B * d.T * p_item);
-  L.psi = off; off += align_up((size_t)d.B * (d.T + 1) * mn * sizeof(cplx));
-  L.lam = off; off += align_up((size_t)d.B * (d.T + 1) * mn * sizeof(cplx));
-  L.gctrl = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
-  L.ot = off; off += align_up((size_t)d.B * (d.T + 1) * sizeof(cplx));
+  L.P = off; off += align_up((size_t)Bc * d.T * p_item);
+  L.psi = off; off += align_up((size_t)Bc * (d.T + 1) * mn * sizeof(cplx));
+  L.lam = off; off += align_up((size_t)Bc * (d.T + 1) * mn * sizeof(cplx));
+  L.gctrl = off; off += align_up((size_t)Bc * d.K * d.T * sizeof(double));
+  L.ot = off; off += align_up((size_t)Bc * (d.T + 1) * sizeof(cplx));
   L.scal = off; off += align_up((size_t)d.B * 8 * sizeof(double));
   L.Ufin = off; off += align_up((size_t)d.B * nn * sizeof(cplx));
   L.st_base = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_grad = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_out = off; off += align_up((size_t)d.B * 4 * sizeof(double));
   L.scratch = off;
-  if (d.n > 64) off += align_up(qoc_large_scratch_elems(d.n, d.B, sm_count) * sizeof(cplx));
+  if (d.n > 64) off += align_up(qoc_large_scratch_elems(d.n, Bc, sm_count) * sizeof(cplx));
   L.total = off;
   return L;
 }
@@ -76,7 +78,26 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
     h->err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
     return QOC_ECUDA;
   }
-  if (d.n > 64 && d.n > 1024) { h->err = "n too large"; return QOC_EINVAL; }
+  if (d.n > 1024) { h->err = "n too large"; return QOC_EINVAL; }
+  {   // batch chunk: the largest Bc <= B whose workspace fits the memory budget
+    size_t free_b = 0, total_b = 0;
+    double budget = 0.0;
+    const char* env = getenv("QOC_B200_MAX_WS_GB");
+    if (env && atof(env) > 0.0) budget = atof(env) * 1e9;
+    else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = 0.8 * (double)free_b;
+    h->Bc = d.B;
+    if (budget > 0.0) {
+      const double w1 = (double)ws_layout(d, h->sm_count, 1).total, wB = (double)ws_layout(d, h->sm_count, d.B).total;
+      if (wB > budget) {
+        const double per = (wB - w1) / (d.B > 1 ? d.B - 1 : 1);
+        long long bc = (long long)((budget - w1) / (per > 0 ? per : 1.0)) + 1;
+        if (bc < 1) bc = 1;
+        if (bc > d.B) bc = d.B;
+        while (bc > 1 && (double)ws_layout(d, h->sm_count, (int)bc).total > budget) --bc;
+        h->Bc = (int)bc;
+      }
+    }
+  }
   if (d.dtype == QOC_TF32X3 && (d.n > 32 || d.K > 15)) {
     h->err = "QOC_TF32X3 (tcgen05 path) supports n <= 32, K <= 15 in this build";
     return QOC_EINVAL;
@@ -102,13 +123,13 @@ const char* qoc_last_error(qoc_handle_t h) { return h ? h->err.c_str() : "null h
 int qoc_workspace_bytes(qoc_handle_t h, size_t* bytes) {
   QOC_CHECK_H(h);
   if (!bytes) return QOC_EINVAL;
-  *bytes = ws_layout(h->d, h->sm_count).total;
+  *bytes = ws_layout(h->d, h->sm_count, h->Bc).total;
   return QOC_OK;
 }
 
 int qoc_set_workspace(qoc_handle_t h, void* dev_ptr, size_t bytes) {
   QOC_CHECK_H(h);
-  const WsLayout L = ws_layout(h->d, h->sm_count);
+  const WsLayout L = ws_layout(h->d, h->sm_count, h->Bc);
   if (!dev_ptr || ((uintptr_t)dev_ptr & 255)) { h->err = "workspace must be 256-byte aligned"; return QOC_EINVAL; }
   if (bytes < L.total) { h->err = "workspace too small"; return QOC_ENOMEM; }
   char* w = (char*)dev_ptr;
@@ -241,7 +262,7 @@ extern "C" int qoc_set_forbid_basis(qoc_handle_t h, const double* W_host, void* 
   if (!W_host) { cudaFree(h->dressW); h->dressW = nullptr; return QOC_OK; }
   const qoc_dims_t& d = h->d;
   CUDA_TRY(h, upload(&h->dressW, W_host, (size_t)d.n * d.n, st));
-  if (!h->psid) CUDA_TRY(h, cudaMalloc((void**)&h->psid, (size_t)d.B * (d.T + 1) * d.m * d.n * sizeof(cplx)));
+  if (!h->psid) CUDA_TRY(h, cudaMalloc((void**)&h->psid, (size_t)h->Bc * (d.T + 1) * d.m * d.n * sizeof(cplx)));
   CUDA_TRY(h, cudaStreamSynchronize(st));
   return QOC_OK;
 }
@@ -279,6 +300,22 @@ static int prof_mark(qoc_handle_t h, int i, cudaStream_t st) {
   return QOC_OK;
 }
 
+// restrict the parameter block to instances [b0, b0 + bc): per-instance user arrays and the persistent
+// scal / Ufin arrays are offset, the chunk-sized workspace arrays are reused from their start
+static QocParams chunk_params(const QocParams& p, const qoc_dims_t& d, int b0, int bc) {
+  QocParams q = p;
+  q.B = bc;
+  q.base = p.base + (size_t)b0 * d.K * d.T;
+  q.scal = p.scal + (size_t)b0 * 8;
+  q.Ufin = p.Ufin + (size_t)b0 * d.n * d.n;
+  if (p.loss) q.loss = p.loss + b0;
+  if (p.reg_loss) q.reg_loss = p.reg_loss + b0;
+  if (p.grad) q.grad = p.grad + (size_t)b0 * d.K * d.T;
+  if (p.unitary_scale) q.unitary_scale = p.unitary_scale + b0;
+  if (p.grad_squared) q.grad_squared = p.grad_squared + b0;
+  return q;
+}
+
 static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   int rc;
   h->ev_recorded = 0;
@@ -307,16 +344,20 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
   p.loss = loss_dev; p.reg_loss = reg_loss_dev; p.grad = grad_dev;
   p.unitary_scale = unitary_scale_dev; p.grad_squared = grad_squared_dev;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = run_forward(h, p, st);
-  if (rc) return rc;
-  if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 1, st, &h->launches));
-  if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, st, &h->launches));
-  else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
-  if ((rc = prof_mark(h, 4, st))) return rc;
-  CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, st, &h->launches));
-  if ((rc = prof_mark(h, 5, st))) return rc;
-  CUDA_TRY(h, qoc_launch_finalize(p, st, &h->launches));
-  if ((rc = prof_mark(h, 6, st))) return rc;
+  const QocParams full = p;
+  for (int b0 = 0; b0 < h->d.B; b0 += h->Bc) {           // one pass per batch chunk (a single pass when everything fits)
+    p = chunk_params(full, h->d, b0, h->d.B - b0 < h->Bc ? h->d.B - b0 : h->Bc);
+    rc = run_forward(h, p, st);
+    if (rc) return rc;
+    if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 1, st, &h->launches));
+    if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, st, &h->launches));
+    else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
+    if ((rc = prof_mark(h, 4, st))) return rc;
+    CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, st, &h->launches));
+    if ((rc = prof_mark(h, 5, st))) return rc;
+    CUDA_TRY(h, qoc_launch_finalize(p, st, &h->launches));
+    if ((rc = prof_mark(h, 6, st))) return rc;
+  }
   return QOC_OK;
 }
 
@@ -327,14 +368,21 @@ int qoc_evolve(qoc_handle_t h, const double* base_dev, double* U_final_dev, doub
   int rc = fill_params(h, p, base_dev);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = run_forward(h, p, st);
-  if (rc) return rc;
   const qoc_dims_t& d = h->d;
+  const QocParams full = p;
+  for (int b0 = 0; b0 < d.B; b0 += h->Bc) {
+    const int bc = d.B - b0 < h->Bc ? d.B - b0 : h->Bc;
+    p = chunk_params(full, d, b0, bc);
+    rc = run_forward(h, p, st);
+    if (rc) return rc;
+    if (inter_vecs_dev) {
+      const size_t per = (size_t)(d.T + 1) * d.m * d.n * 2;      // doubles per instance
+      CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_dev + (size_t)b0 * per, h->psi, (size_t)bc * per * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, st));
+    }
+  }
   if (U_final_dev)
     CUDA_TRY(h, cudaMemcpyAsync(U_final_dev, h->Ufin, (size_t)d.B * d.n * d.n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-  if (inter_vecs_dev)
-    CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_dev, h->psi, (size_t)d.B * (d.T + 1) * d.m * d.n * sizeof(cplx),
-                                cudaMemcpyDeviceToDevice, st));
   if (loss_dev)
     CUDA_TRY(h, cudaMemcpy2DAsync(loss_dev, sizeof(double), h->scal + 2, 8 * sizeof(double), sizeof(double), d.B,
                                   cudaMemcpyDeviceToDevice, st));
@@ -376,13 +424,32 @@ int qoc_evolve_host(qoc_handle_t h, const double* base_host, double* U_final_hos
   const size_t nb = (size_t)d.B * d.K * d.T * sizeof(double);
   CUDA_TRY(h, cudaMemcpyAsync(h->st_base, base_host, nb, cudaMemcpyHostToDevice, st));
   double* o = h->st_out;
-  int rc = qoc_evolve(h, h->st_base, nullptr, nullptr, o, o + d.B, stream);
-  if (rc) return rc;
+  int rc = QOC_OK;
+  if (h->Bc >= d.B || !inter_vecs_host) {
+    rc = qoc_evolve(h, h->st_base, nullptr, nullptr, o, o + d.B, stream);
+    if (rc) return rc;
+    if (inter_vecs_host)
+      CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_host, h->psi, (size_t)d.B * (d.T + 1) * d.m * d.n * sizeof(cplx),
+                                  cudaMemcpyDeviceToHost, st));
+  } else {                                               // chunked: stream each pass's states to the host
+    QocParams p;
+    rc = fill_params(h, p, h->st_base);
+    if (rc) return rc;
+    const QocParams full = p;
+    const size_t per = (size_t)(d.T + 1) * d.m * d.n * 2;
+    for (int b0 = 0; b0 < d.B; b0 += h->Bc) {
+      const int bc = d.B - b0 < h->Bc ? d.B - b0 : h->Bc;
+      p = chunk_params(full, d, b0, bc);
+      rc = run_forward(h, p, st);
+      if (rc) return rc;
+      CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_host + (size_t)b0 * per, h->psi, (size_t)bc * per * sizeof(double),
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(h, cudaMemcpy2DAsync(o, sizeof(double), h->scal + 2, 8 * sizeof(double), sizeof(double), d.B, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(h, cudaMemcpy2DAsync(o + d.B, sizeof(double), h->scal + 5, 8 * sizeof(double), sizeof(double), d.B, cudaMemcpyDeviceToDevice, st));
+  }
   if (U_final_host)
     CUDA_TRY(h, cudaMemcpyAsync(U_final_host, h->Ufin, (size_t)d.B * d.n * d.n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
-  if (inter_vecs_host)
-    CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_host, h->psi, (size_t)d.B * (d.T + 1) * d.m * d.n * sizeof(cplx),
-                                cudaMemcpyDeviceToHost, st));
   if (loss_host) CUDA_TRY(h, cudaMemcpyAsync(loss_host, o, d.B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (unitary_scale_host)
     CUDA_TRY(h, cudaMemcpyAsync(unitary_scale_host, o + d.B, d.B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -399,6 +466,8 @@ int qoc_debug_propagators(qoc_handle_t h, void** P_dev, int* elem_bytes) {
 }
 
 int64_t qoc_launch_count(qoc_handle_t h) { return h ? h->launches : -1; }
+
+int qoc_batch_chunk(qoc_handle_t h) { return h ? h->Bc : -1; }
 
 int qoc_poll_error(qoc_handle_t h, void* stream) {
   QOC_CHECK_H(h);

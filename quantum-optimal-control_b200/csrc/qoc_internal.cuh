@@ -52,6 +52,7 @@ struct QocParams {
 struct qoc_handle_s {
   qoc_dims_t d;
   int NP;
+  int Bc;                                 // instances per pass (batch chunk), <= d.B
   std::string err;
   int sm_count;
   bool problem_set, ws_set;
