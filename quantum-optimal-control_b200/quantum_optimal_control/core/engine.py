@@ -19,7 +19,7 @@ _DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF
 SYMBOLS = ["qoc_abi_version", "qoc_create", "qoc_destroy", "qoc_last_error", "qoc_workspace_bytes",
            "qoc_set_workspace", "qoc_set_problem", "qoc_set_regularizers", "qoc_value_and_grad", "qoc_evolve",
            "qoc_value_and_grad_host", "qoc_evolve_host", "qoc_debug_propagators", "qoc_launch_count", "qoc_set_profiling",
-           "qoc_kernel_times_ms", "qoc_poll_error", "qoc_set_forbid_basis"]
+           "qoc_kernel_times_ms", "qoc_poll_error", "qoc_set_forbid_basis", "qoc_batch_chunk"]
 
 
 class QocDims(C.Structure):
@@ -71,6 +71,7 @@ def load_library(path=None):
     lib.qoc_launch_count.argtypes = [vp]
     lib.qoc_launch_count.restype = C.c_int64
     lib.qoc_poll_error.argtypes = [vp, vp]
+    lib.qoc_batch_chunk.argtypes = [vp]
     lib.qoc_set_forbid_basis.argtypes = [vp, dp, vp]
     lib.qoc_set_profiling.argtypes = [vp, C.c_int]
     lib.qoc_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -133,6 +134,7 @@ class GrapeEngine:
             nbytes = C.c_size_t()
             self._check(self.lib.qoc_workspace_bytes(self._h, C.byref(nbytes)))
             self.workspace_bytes = nbytes.value
+            self.batch_chunk = int(self.lib.qoc_batch_chunk(self._h))
             self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
             ptr = (self._ws.data_ptr() + 255) // 256 * 256
             self._check(self.lib.qoc_set_workspace(self._h, C.c_void_p(ptr), C.c_size_t(nbytes.value)))

@@ -343,3 +343,31 @@ def test_full_size_c3_properties(built_lib):
         assert abs(out['reg_loss'][b].item() - ref.reg_loss) < 1e-9
         assert np.abs(out['grad'][b].cpu().numpy() - ref.grad).max() < 1e-9 * np.abs(ref.grad).max()
     eng.close()
+
+
+def test_batch_chunking_gives_identical_results(built_lib, monkeypatch):
+    """A workspace budget smaller than the full batch makes the library process the batch in chunks
+    (qoc_batch_chunk < B); every output must be bit-identical to the single-pass run."""
+    pb = dict(W.c2_transmon_cavity(T=16), total_time=32.0)
+    pb['reg_coeffs'] = {'dwdt': 0.1, 'forbidden_coeff_list': [1.0], 'states_forbidden_list': [20]}
+    setups, guess, args, kw = make_case(pb, seed=77, B=7)
+    sp, eng = engine_for(args, kw, guess)
+    assert eng.batch_chunk == 7
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    ref = {k: v.clone() for k, v in eng.value_and_grad(base).items()}
+    ev_ref = {k: (None if v is None else v.clone()) for k, v in eng.evolve(base).items()}
+    evh_ref = eng.evolve_host(sp.ops_weight_base)
+    need = eng.workspace_bytes
+    eng.close()
+    monkeypatch.setenv("QOC_B200_MAX_WS_GB", str(need * 0.45 / 1e9))
+    sp2, eng2 = engine_for(args, kw, guess)
+    assert 1 <= eng2.batch_chunk < 7 and eng2.workspace_bytes < need
+    out = eng2.value_and_grad(base)
+    ev = eng2.evolve(base)
+    evh = eng2.evolve_host(sp.ops_weight_base)
+    for k in ref:
+        assert torch.equal(out[k], ref[k]), k
+    for k in ('U_final', 'inter_vecs', 'loss', 'unitary_scale'):
+        assert torch.equal(ev[k], ev_ref[k]), k
+        assert np.array_equal(evh[k], evh_ref[k]), k
+    eng2.close()
