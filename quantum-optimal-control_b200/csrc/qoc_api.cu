@@ -350,10 +350,15 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
     rc = run_forward(h, p, st);
     if (rc) return rc;
     if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 1, st, &h->launches));
+    // dense-m problems (m >= NP/2, dense controls) take the DMMA costate / gradient kernels
+    const bool dense_m = h->d.n <= 64 && h->d.dtype == QOC_F64 && 2 * h->d.m >= h->NP && h->d.m <= h->NP;
+    const bool dense_A = (double)h->nnz >= 0.25 * (double)h->d.K * h->d.n * h->d.n;
     if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, st, &h->launches));
+    else if (dense_m) CUDA_TRY(h, qoc_launch_costate_mma(p, h->NP, st, &h->launches));
     else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
     if ((rc = prof_mark(h, 4, st))) return rc;
-    CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, st, &h->launches));
+    if (dense_m && dense_A) CUDA_TRY(h, qoc_launch_grad_mma(p, h->NP, h->sm_count, st, &h->launches));
+    else CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, st, &h->launches));
     if ((rc = prof_mark(h, 5, st))) return rc;
     CUDA_TRY(h, qoc_launch_finalize(p, st, &h->launches));
     if ((rc = prof_mark(h, 6, st))) return rc;

@@ -86,6 +86,8 @@ cudaError_t qoc_launch_expm_large(const QocParams& p, int sm_count, void* scratc
 cudaError_t qoc_launch_chain_large(const QocParams& p, void* scratch, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate_large(const QocParams& p, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_dress(const QocParams& p, int phase, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_costate_mma(const QocParams& p, int NP, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_grad_mma(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_grad(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches);

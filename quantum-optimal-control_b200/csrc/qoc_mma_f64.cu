@@ -575,6 +575,252 @@ cudaError_t launch_chain(const QocParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense-m variants (m >= NP/2, e.g. config C5 with m = n): the costate sweep and the control
+// gradient are GEMM-shaped too and run on the same DMMA machinery.
+//   k_costate_mma : Lambda(t) = P_t^dagger Lambda(t+1) + S(t), Lambda = [n x m] (columns = states)
+//   k_grad_mma    : W = Lambda(t+1)^dagger-ish outer sum  W[a][c] = sum_j conj(lam_j[a]) psi_j[c],
+//                   g_k = Re sum_ac A_k[a][c] W[a][c]      (matexp_op_grad, tensorflow_state.py:49-65)
+// ---------------------------------------------------------------------------------------------
+// C = A^H * B: the A fragment (row r, k) = conj(A[k][r]) is read with the B-fragment pattern
+template <int NP, int RB, int CB>
+DEVINL void mma_gemm_ah(const cplx* __restrict__ A, const cplx* __restrict__ B, double (&cr)[RB][CB][2],
+                        double (&ci)[RB][CB][2], int rb0, int cb0, int ksteps, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < CB; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+  const int ac = 8 * rb0 + g, bc = 8 * cb0 + g;
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k = 4 * ks + q;
+    const int km = sw_mask(k);
+    const cplx* Arow = A + k * NP;
+    const cplx* Brow = B + k * NP;
+    cplx a[RB], b[CB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) { a[i] = Arow[(ac + 8 * i) ^ km]; a[i].y = -a[i].y; }
+#pragma unroll
+    for (int j = 0; j < CB; ++j) b[j] = Brow[(bc + 8 * j) ^ km];
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const double nai = -a[i].y;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], nai, b[j].y);
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
+  }
+}
+
+template <int NP, int RB, int CB, int NPB, int NLB>
+__global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_costate_mma(QocParams p) {
+  typedef MT<NP, RB, CB> T_;
+  constexpr int G = T_::THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* Pb = reinterpret_cast<cplx*>(smem_raw);           // [NPB][MAT]
+  cplx* Lb = Pb + NPB * T_::MAT;                          // [NLB][MAT]  Lambda[r][j]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
+  const int n = p.n, T = p.T, m = p.m, nn = n * n, mn = m * n;
+  const int ksteps = (n + 3) >> 2;
+  const int b = blockIdx.x;
+  const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * nn;
+  const cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
+  cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn;
+  const double* sc = p.scal + (size_t)b * 8;
+  const double o_re = sc[0], o_im = sc[1], spdfac = sc[4];
+  const bool forb = p.reg.has_forbidden && p.fw != nullptr;
+  const bool spd = p.reg.has_speed_up != 0;
+  const double m2 = (double)m * (double)m;
+
+  auto source = [&](int t, int j, int r) -> cplx {       // S(t)[r][j]
+    cplx s = make_double2(0.0, 0.0);
+    if (forb && p.dressW) {
+      const cplx d = p.psid[((size_t)b * (T + 1) + t) * mn + (size_t)j * n + r];
+      s.x += d.x; s.y += d.y;
+    } else if (forb) {
+      const cplx x = psi_b[(size_t)t * mn + (size_t)j * n + r];
+      const double pop = x.x * x.x + x.y * x.y;
+      const double c = p.fw[r] / (double)T * 2.0 * pop;
+      s.x += c * x.x; s.y += c * x.y;
+    }
+    if (spd) {
+      const cplx o = p.ot[(size_t)b * (T + 1) + t];
+      const cplx ph = p.phi[(size_t)j * n + r];
+      s.x += spdfac * (o.x * ph.x - o.y * ph.y); s.y += spdfac * (o.x * ph.y + o.y * ph.x);
+    }
+    return s;
+  };
+  auto prefetch = [&](int t) {
+    if (t >= 1) {
+      const cplx* src = Pg + (size_t)t * nn;
+      cplx* dst = Pb + (t % NPB) * T_::MAT;
+      for (int idx = tid; idx < nn; idx += G) {
+        const int r = idx / n, c = idx - r * n;
+        cp_async16(dst + swz<NP>(r, c), src + idx);
+      }
+    }
+    cp_async_commit();
+  };
+
+  for (int i = tid; i < (NPB + NLB) * T_::MAT; i += G) Pb[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int idx = tid; idx < mn; idx += G) {                // Lambda(T) = -(2/m^2) o phi + S(T)
+    const int j = idx / n, r = idx - j * n;
+    const cplx ph = p.phi[idx];
+    cplx l = make_double2((o_re * ph.x - o_im * ph.y) * (-2.0 / m2), (o_re * ph.y + o_im * ph.x) * (-2.0 / m2));
+    const cplx s = source(T, j, r);
+    l.x += s.x; l.y += s.y;
+    Lb[swz<NP>(r, j)] = l;
+    lam_b[(size_t)T * mn + idx] = l;
+  }
+#pragma unroll
+  for (int i = 0; i < NPB - 1; ++i) prefetch(T - 1 - i);
+  int cur = 0;
+  for (int t = T - 1; t >= 1; --t) {
+    cp_async_wait<NPB - 2>();
+    __syncthreads();
+    prefetch(t - (NPB - 1));
+    const cplx* Lc = Lb + (NLB == 2 ? cur : 0) * T_::MAT;
+    cplx* Ln = Lb + (NLB == 2 ? (cur ^ 1) : 0) * T_::MAT;
+    double cr[RB][CB][2], ci[RB][CB][2];
+    mma_gemm_ah<NP, RB, CB>(Pb + (t % NPB) * T_::MAT, Lc, cr, ci, rb0, cb0, ksteps, lane);
+    if (NLB == 1) __syncthreads();                    // in-place update: every warp has finished reading Lambda
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = 8 * (rb0 + i) + g;
+#pragma unroll
+      for (int jj = 0; jj < CB; ++jj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = 8 * (cb0 + jj) + 2 * q + e;
+          cplx l = make_double2(cr[i][jj][e], ci[i][jj][e]);
+          if (r < n && j < m) {
+            const cplx s = source(t, j, r);
+            l.x += s.x; l.y += s.y;
+            lam_b[(size_t)t * mn + (size_t)j * n + r] = l;
+          } else {
+            l = make_double2(0.0, 0.0);
+          }
+          Ln[swz<NP>(r, j)] = l;
+        }
+    }
+    cur ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+template <int NP, int RB, int CB>
+__global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_grad_mma(QocParams p) {
+  typedef MT<NP, RB, CB> T_;
+  constexpr int G = T_::THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* Ls = reinterpret_cast<cplx*>(smem_raw);           // [MAT]  L[j][a] = lam_j(t+1)[a]
+  cplx* Ys = Ls + T_::MAT;                                // [MAT]  Y[j][c] = psi_j(t+1)[c]
+  __shared__ double red[32 * 8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
+  const int n = p.n, T = p.T, m = p.m, K = p.K, nn = n * n, mn = m * n;
+  const int ksteps = (m + 3) >> 2;
+  const long long items = (long long)p.B * T;
+  for (int i = tid; i < 2 * T_::MAT; i += G) Ls[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = (int)(item / T), t = (int)(item % T);
+    const size_t off = ((size_t)b * (T + 1) + (t + 1)) * mn;
+    for (int idx = tid; idx < mn; idx += G) {
+      const int j = idx / n, i = idx - j * n;
+      cp_async16(Ls + swz<NP>(j, i), p.lam + off + idx);
+      cp_async16(Ys + swz<NP>(j, i), p.psi + off + idx);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double wr[RB][CB][2], wi[RB][CB][2];
+    mma_gemm_ah<NP, RB, CB>(Ls, Ys, wr, wi, rb0, cb0, ksteps, lane);
+    for (int k0 = 0; k0 < K; k0 += 8) {                   // up to 8 controls per reduction round
+      double part[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) part[kk] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        if (k0 + kk < K) {
+          const cplx* Ak = p.A + (size_t)(k0 + kk + 1) * nn;
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int a = 8 * (rb0 + i) + g;
+#pragma unroll
+            for (int jj = 0; jj < CB; ++jj)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = 8 * (cb0 + jj) + 2 * q + e;
+                if (a < n && c < n) {
+                  const cplx av = __ldg(Ak + (size_t)a * n + c);
+                  s += av.x * wr[i][jj][e] - av.y * wi[i][jj][e];
+                }
+              }
+          }
+          part[kk] = warp_sum_d(s);
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) red[warp * 8 + kk] = part[kk];
+      }
+      __syncthreads();
+      if (tid < 8 && k0 + tid < K) {
+        double s = 0.0;
+        for (int w = 0; w < T_::WARPS; ++w) s += red[w * 8 + tid];
+        p.gctrl[((size_t)b * K + k0 + tid) * T + t] = s;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int NP, int RB, int CB, int NPB, int NLB>
+cudaError_t launch_costate_mma(const QocParams& p, cudaStream_t st) {
+  typedef MT<NP, RB, CB> T_;
+  static_assert(NPB >= 2, "prefetch needs two propagator buffers");
+  const size_t smem = (size_t)(NPB + NLB) * T_::MAT * sizeof(cplx);
+  cudaError_t e = cudaFuncSetAttribute(k_costate_mma<NP, RB, CB, NPB, NLB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_costate_mma<NP, RB, CB, NPB, NLB><<<p.B, T_::THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int NP, int RB, int CB>
+cudaError_t launch_grad_mma(const QocParams& p, int sm_count, cudaStream_t st) {
+  typedef MT<NP, RB, CB> T_;
+  const size_t smem = (size_t)2 * T_::MAT * sizeof(cplx);
+  cudaError_t e = cudaFuncSetAttribute(k_grad_mma<NP, RB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_grad_mma<NP, RB, CB>, T_::THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const long long items = (long long)p.B * p.T;
+  long long grid = (long long)sm_count * occ;
+  if (grid > items) grid = items;
+  k_grad_mma<NP, RB, CB><<<(unsigned)grid, T_::THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches) {
@@ -614,4 +860,39 @@ cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaS
     case 64: return launch_chain<64, 2, 4, 2, 1>(p, st);      // 3 x 64 KB: X updated in place
   }
   return cudaErrorInvalidValue;
+}
+
+// dense-m (m >= NP/2) costate / gradient on the DMMA path; returns cudaErrorNotSupported when not applicable
+cudaError_t qoc_launch_costate_mma(const QocParams& p, int NP, cudaStream_t st, int64_t* launches) {
+  if (2 * p.m < NP || p.m > NP) return cudaErrorNotSupported;
+  ++*launches;
+  switch (NP) {
+    case 8: return launch_costate_mma<8, 1, 1, 3, 2>(p, st);
+    case 16: return launch_costate_mma<16, 1, 1, 3, 2>(p, st);
+    case 24: return launch_costate_mma<24, 1, 1, 3, 2>(p, st);
+    case 32: return launch_costate_mma<32, 1, 2, 3, 2>(p, st);
+    case 40: return launch_costate_mma<40, 1, 5, 3, 2>(p, st);
+    case 48: return launch_costate_mma<48, 1, 3, 3, 2>(p, st);
+    case 56: return launch_costate_mma<56, 1, 7, 2, 2>(p, st);
+    case 64: return launch_costate_mma<64, 2, 4, 2, 1>(p, st);
+  }
+  --*launches;
+  return cudaErrorNotSupported;
+}
+
+cudaError_t qoc_launch_grad_mma(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches) {
+  if (2 * p.m < NP || p.m > NP) return cudaErrorNotSupported;
+  ++*launches;
+  switch (NP) {
+    case 8: return launch_grad_mma<8, 1, 1>(p, sm_count, st);
+    case 16: return launch_grad_mma<16, 1, 1>(p, sm_count, st);
+    case 24: return launch_grad_mma<24, 1, 1>(p, sm_count, st);
+    case 32: return launch_grad_mma<32, 1, 2>(p, sm_count, st);
+    case 40: return launch_grad_mma<40, 1, 5>(p, sm_count, st);
+    case 48: return launch_grad_mma<48, 1, 3>(p, sm_count, st);
+    case 56: return launch_grad_mma<56, 1, 7>(p, sm_count, st);
+    case 64: return launch_grad_mma<64, 2, 4>(p, sm_count, st);
+  }
+  --*launches;
+  return cudaErrorNotSupported;
 }
