@@ -40,34 +40,31 @@ class TF1AdamState:
 
 
 class TF1AdamHost:
-    """NumPy twin of :class:`TF1AdamState` for callers that keep the weights on the host and go
-    through the host-buffer C-ABI entry point (``GrapeEngine.value_and_grad_host``)."""
+    """Host twin of :class:`TF1AdamState` for callers that keep the weights on the host and go through the
+    host-buffer C-ABI entry point (``GrapeEngine.value_and_grad_host``).  ``theta`` / ``grad`` are NumPy arrays
+    (typically the pinned ``host_buffers()``); the update runs in place through torch-CPU views of them so it is
+    multi-threaded and allocation-free."""
 
     def __init__(self, shape, beta1=0.9, beta2=0.999, eps=1e-8):
-        self.m = np.zeros(shape)
-        self.v = np.zeros(shape)
+        import torch
+        self.torch = torch
+        self.m = torch.zeros(tuple(shape), dtype=torch.float64)
+        self.v = torch.zeros(tuple(shape), dtype=torch.float64)
+        self.tmp = torch.empty(tuple(shape), dtype=torch.float64)
         self.t = 0
         self.b1, self.b2, self.eps = beta1, beta2, eps
 
     def step(self, theta, grad, lr):
-        """In-place update of ``theta`` (returned for convenience); no temporaries beyond one scratch array."""
+        torch = self.torch
         self.t += 1
         lr_t = lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
-        if getattr(self, '_tmp', None) is None or self._tmp.shape != grad.shape:
-            self._tmp = np.empty_like(self.m)
-        tmp = self._tmp
-        self.m *= self.b1
-        np.multiply(grad, 1.0 - self.b1, out=tmp)
-        self.m += tmp
-        self.v *= self.b2
-        np.multiply(grad, grad, out=tmp)
-        tmp *= (1.0 - self.b2)
-        self.v += tmp
-        np.sqrt(self.v, out=tmp)
-        tmp += self.eps
-        np.divide(self.m, tmp, out=tmp)
-        tmp *= lr_t
-        theta -= tmp
+        th = torch.from_numpy(theta)
+        g = torch.from_numpy(np.ascontiguousarray(grad))
+        self.m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+        self.v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+        torch.sqrt(self.v, out=self.tmp)
+        self.tmp.add_(self.eps)
+        th.addcdiv_(self.m, self.tmp, value=-lr_t)
         return theta
 
 

@@ -371,3 +371,45 @@ def test_batch_chunking_gives_identical_results(built_lib, monkeypatch):
         assert torch.equal(ev[k], ev_ref[k]), k
         assert np.array_equal(evh[k], evh_ref[k]), k
     eng2.close()
+
+
+_NCCL = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "quantum-optimal-control_b200")); sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+rank = int(sys.argv[1]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=2, device_id=torch.device("cuda", rank))
+import workloads as W
+from quantum_optimal_control.main_grape.grape import Grape
+from quantum_optimal_control.core.population import grape_population
+pb = W.c1_pi_pulse(T=30); args, kw = W.grape_kwargs(pb)
+g = W.random_guess(2, 30, pb["maxA"], 3, B=5)
+conv = {"rate": 0.02, "update_step": 50, "max_iterations": 10, "conv_target": 1e-12, "learning_rate_decay": 100}
+res = grape_population(Grape, args, g, convergence=conv, save=False, show_plots=False, quiet=True, **kw)
+if rank == 0:
+    np.savez(sys.argv[2], best=res["best"], loss=res["loss"], uks=res["uks"], U=res["U_final"])
+dist.destroy_process_group()
+'''
+
+
+def test_population_sweep_two_gpus_nccl(built_lib, tmp_path):
+    """Batch sharded over 2 GPUs, one NCCL all-gather of the losses + broadcast of the winner (needs 2 GPUs)."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from quantum_optimal_control.main_grape.grape import Grape
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "nccl_pop.py"
+    out = tmp_path / "res.npz"
+    script.write_text(_NCCL % dict(root=root, port=29650 + os.getpid() % 200))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(out)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    res = np.load(out)
+    pb = W.c1_pi_pulse(T=30)
+    args, kw = W.grape_kwargs(pb)
+    g = W.random_guess(2, 30, pb['maxA'], 3, B=5)
+    conv = {"rate": 0.02, "update_step": 50, "max_iterations": 10, "conv_target": 1e-12, "learning_rate_decay": 100}
+    uks, Uf, losses = Grape(*args, initial_guess=g, convergence=conv, save=False, show_plots=False, quiet=True, return_losses=True, **kw)
+    assert np.allclose(res['loss'], losses, atol=1e-12) and int(res['best']) == int(np.argmin(losses))
+    assert np.allclose(res['uks'], uks[int(res['best'])], atol=1e-12)

@@ -187,3 +187,16 @@ def test_population_sweep_world_size_2_gloo(tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_host_adam_matches_tf1_formula():
+    from quantum_optimal_control.core.optimizer import TF1AdamHost
+    rng = np.random.default_rng(0)
+    th = rng.normal(size=(3, 4, 5))
+    th2 = th.copy()
+    a, b = TF1AdamHost(th.shape), O.TF1Adam(th.shape)
+    for i in range(6):
+        g = rng.normal(size=th.shape)
+        a.step(th, g, 0.01 * (i + 1))
+        th2 = b.step(th2, g, 0.01 * (i + 1))
+    assert np.abs(th - th2).max() < 1e-15
