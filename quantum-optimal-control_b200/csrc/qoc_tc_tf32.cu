@@ -13,12 +13,17 @@
 // a product is three MMAs  A_lo B_hi + A_hi B_lo + A_hi B_hi  accumulated in fp32 in TMEM
 // ("3xTF32"), giving ~fp32 accuracy -- the reference itself is float32.
 //
-// Data flow per product: operands live in shared memory in the canonical K-major SWIZZLE_128B UMMA
-// layout (written by generic stores from registers, then fence.proxy.async); one elected thread
-// issues 2 x 24 tcgen05.mma and a tcgen05.commit onto an mbarrier; all threads wait, pull their
-// accumulator row with tcgen05.ld (32x32b.x32), apply the Paterson-Stockmeyer update in registers,
-// re-split and write the next operands.  Two CTAs are resident per SM so one CTA's epilogue overlaps
-// the other's MMAs.  Layouts and descriptors were validated on hardware with tools/tc_probe.cu.
+// Data flow per product: the A operand (the 64 x 64 embedding, hi and lo parts) lives in TENSOR MEMORY
+// next to the accumulator -- row rho of A sits in the same TMEM lane as row rho of D, so the thread that
+// pulled accumulator row rho with tcgen05.ld writes the next A row straight back with tcgen05.st (the
+// Im/Re partner row comes through a small shared-memory exchange).  Only the B operand [Yr;Yi]^T goes
+// through shared memory (canonical K-major SWIZZLE_128B UMMA layout, generic stores + fence.proxy.async).
+// A converged warp issues the 2 x 24 tcgen05.mma (A from TMEM, B from a shared-memory descriptor) with
+// elect.sync and a tcgen05.commit onto an mbarrier; all threads wait, tcgen05.ld their row, apply the
+// Paterson-Stockmeyer update in registers, re-split and write the next operands.  Two CTAs are resident
+// per SM (2 x 256 TMEM columns) so one CTA's epilogue overlaps the other's MMAs.  v1 kept A in shared
+// memory too and was shared-memory-bandwidth bound (profiles/r01_ncu_expm_tc32.md).  Layouts, descriptors
+// and the A-in-TMEM lane map were validated on hardware with tools/tc_probe.cu (modes 32 and 40).
 //
 // Output: P[b][t] as fp32 planar padded [2][32][32] (Re plane, Im plane), rows 128-byte aligned.
 #include "qoc_internal.cuh"
@@ -29,10 +34,14 @@
 namespace {
 
 constexpr int NP = 32;
-constexpr uint32_t A_BYTES = 64 * 64 * 4;      // one A-form operand (hi or lo)
-constexpr uint32_t B_BYTES = 32 * 64 * 4;      // one B-form operand
-constexpr uint32_t ITEM_BYTES = 2 * A_BYTES + 2 * B_BYTES;      // 48 KB
+constexpr uint32_t B_BYTES = 32 * 64 * 4;      // one B-form operand (hi or lo)
+constexpr int XLD = 36;                        // exchange-buffer row stride (floats, 16-byte aligned rows)
+constexpr uint32_t X_BYTES = 64 * XLD * 4;     // row exchange buffer (9 KB)
+constexpr uint32_t ITEM_BYTES = 2 * B_BYTES + 10240;            // B_hi | B_lo | exchange  (26 KB, 1024-aligned)
 constexpr int STG_LD = 33;                     // staging row stride (floats)
+constexpr uint32_t TM_COLS = 256;              // TMEM columns per CTA: D [0,32) | A_hi [32,96) | A_lo [96,160)
+constexpr uint32_t TM_AHI = 32, TM_ALO = 96;
+constexpr size_t SMEM_REQ = 110 * 1024;        // > 227/3 KB: caps residency at 2 CTAs/SM (2 x 256 TMEM columns)
 // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2 at bits 7-9 / 10-12), both K-major,
 // N>>3 at bits 17-22, M>>4 at bits 24-28
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((64u >> 4) << 24);
@@ -50,11 +59,23 @@ DEVINL uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
-DEVINL void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+DEVINL void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+
+DEVINL void tmem_st32(uint32_t taddr, const uint32_t (&u)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]), "r"(u[10]),
+      "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]), "r"(u[18]), "r"(u[19]), "r"(u[20]),
+      "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]),
+      "r"(u[31])
       : "memory");
 }
 
@@ -80,49 +101,60 @@ DEVINL void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
-// byte offset of element chunk (row, 16-byte chunk cc in the 32-element k-block kb) of an A-form operand
-DEVINL uint32_t a_off(int row, int kb, int cc) {
-  return (uint32_t)(kb * 8192 + (row >> 3) * 1024 + (row & 7) * 128 + ((cc ^ (row & 7)) << 4));
-}
 // byte offset of element (n, k) of a B-form operand (B^T, 32 rows n, K = 64 in two k-blocks)
 DEVINL uint32_t b_off(int n, int k) {
   return (uint32_t)((k >> 5) * 4096 + (n >> 3) * 1024 + (n & 7) * 128 + ((((k & 31) >> 2) ^ (n & 7)) << 4) + (k & 3) * 4);
 }
 
-// write this thread's stacked row rho (rho < 32: Re row rho, else Im row rho-32) of a matrix into the
-// embedded A-form [[Xr,-Xi],[Xi,Xr]] (hi and lo) and / or the B-form [Xr; Xi]^T.
 DEVINL void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 DEVINL void sts32(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+DEVINL float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
-template <bool WA, bool WB>
-DEVINL void write_operands(uint32_t sA_hi, uint32_t sB_hi, int rho, const float (&v)[32]) {
-  const uint32_t sA_lo = sA_hi + A_BYTES;
+// B-form [Xr; Xi]^T (hi and lo) from this thread's stacked row rho (rho < 32: Re row rho, else Im row rho-32)
+DEVINL void write_b_operand(uint32_t sB_hi, int rho, const float (&v)[32]) {
   const uint32_t sB_lo = sB_hi + B_BYTES;
-  const int row2 = rho < 32 ? rho + 32 : rho - 32;
-  const float sgn = rho < 32 ? 1.0f : -1.0f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    float hi, lo;
+    split_tf32(v[c], hi, lo);
+    const uint32_t o = b_off(c, rho);
+    sts32(sB_hi + o, hi);
+    sts32(sB_lo + o, lo);
+  }
+}
+
+// publish this thread's row to the exchange buffer (read by the Re/Im partner thread after a barrier)
+DEVINL void publish_row(uint32_t sX, int rho, const float (&v)[32]) {
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) sts128(sX + (rho * XLD + 4 * cc) * 4, v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
+}
+
+// A-form row rho of the embedding [[Xr,-Xi],[Xi,Xr]] into TMEM: columns 0-31 = own row, 32-63 = partner row
+// (negated for Re rows), split into hi (TM_AHI) and lo (TM_ALO) tf32 parts.
+DEVINL void write_a_operand(uint32_t ta_lane, uint32_t sX, int rho, const float (&v)[32]) {
+  const int prow = rho < 32 ? rho + 32 : rho - 32;
+  const float sgn = rho < 32 ? -1.0f : 1.0f;
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) { float h, l; split_tf32(v[c], h, l); hi[c] = __float_as_uint(h); lo[c] = __float_as_uint(l); }
+  tmem_st32(ta_lane + TM_AHI, hi);
+  tmem_st32(ta_lane + TM_ALO, lo);
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
-    float hi[4], lo[4];
+    const float4 pv = lds128(sX + (prow * XLD + 4 * cc) * 4);
+    const float x[4] = {sgn * pv.x, sgn * pv.y, sgn * pv.z, sgn * pv.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) split_tf32(v[4 * cc + e], hi[e], lo[e]);
-    if (WA) {
-      const uint32_t o1 = a_off(rho, 0, cc), o2 = a_off(row2, 1, cc);
-      sts128(sA_hi + o1, hi[0], hi[1], hi[2], hi[3]);
-      sts128(sA_lo + o1, lo[0], lo[1], lo[2], lo[3]);
-      sts128(sA_hi + o2, sgn * hi[0], sgn * hi[1], sgn * hi[2], sgn * hi[3]);
-      sts128(sA_lo + o2, sgn * lo[0], sgn * lo[1], sgn * lo[2], sgn * lo[3]);
-    }
-    if (WB) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t o = b_off(4 * cc + e, rho);
-        sts32(sB_hi + o, hi[e]);
-        sts32(sB_lo + o, lo[e]);
-      }
-    }
+    for (int e = 0; e < 4; ++e) { float h, l; split_tf32(x[e], h, l); hi[4 * cc + e] = __float_as_uint(h); lo[4 * cc + e] = __float_as_uint(l); }
   }
+  tmem_st32(ta_lane + TM_AHI + 32, hi);
+  tmem_st32(ta_lane + TM_ALO + 32, lo);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag) {
@@ -134,16 +166,16 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int it = lane >> 4;                      // which item of the pair this thread serves
   const int rho = 16 * warp + (lane & 15);       // stacked accumulator row
-  const uint32_t sA = smem_u32(smem) + it * ITEM_BYTES;    // A_hi | A_lo | B_hi | B_lo (shared-window addresses)
-  const uint32_t sB = sA + 2 * A_BYTES;
-  const float* stg = reinterpret_cast<const float*>(smem + it * ITEM_BYTES + 2 * A_BYTES);   // H staging [64][33] aliases the B-form region
+  const uint32_t sB = smem_u32(smem) + it * ITEM_BYTES;    // B_hi | B_lo | exchange (shared-window addresses)
+  const uint32_t sX = sB + 2 * B_BYTES;
+  const float* stg = reinterpret_cast<const float*>(smem + it * ITEM_BYTES);   // H staging [64][33] aliases the B-form region
   const int n = p.n, K = p.K, T = p.T;
   const long long items = (long long)p.B * T;
   const long long pairs = (items + 1) >> 1;
   float* Pout = reinterpret_cast<float*>(p.P);
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(32) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -151,7 +183,7 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t taddr = *(volatile uint32_t*)&tmem_base_s;
-  const uint32_t ld_addr = taddr + ((uint32_t)(32 * warp) << 16);
+  const uint32_t ld_addr = taddr + ((uint32_t)(32 * warp) << 16);     // this thread's TMEM lane, column 0 (D)
   uint32_t parity = 0;
   bool dead = false;
 
@@ -171,16 +203,14 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
      if (elected) {
       for (int i = 0; i < nvalid; ++i) {
         const uint32_t base = sbase + i * ITEM_BYTES;
-        const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + A_BYTES);
-        const uint64_t b_hi = make_desc(base + 2 * A_BYTES), b_lo = make_desc(base + 2 * A_BYTES + B_BYTES);
-        const uint32_t d = tbase + ((uint32_t)(16 * i) << 16);
+        const uint64_t b_hi = make_desc(base), b_lo = make_desc(base + B_BYTES);
+        const uint32_t d = tbase + ((uint32_t)(16 * i) << 16);          // accumulator / A rows of item i: lane offset 16*i
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ao = (uint64_t)((ks & 3) * 2 + (ks >> 2) * (8192 >> 4));
           const uint64_t bo = (uint64_t)((ks & 3) * 2 + (ks >> 2) * (4096 >> 4));
-          mma_tf32(d, a_lo + ao, b_hi + bo, ks > 0 ? 1u : 0u);
-          mma_tf32(d, a_hi + ao, b_lo + bo, 1u);
-          mma_tf32(d, a_hi + ao, b_hi + bo, 1u);
+          mma_tf32_ts(d, d + TM_ALO + 8 * ks, b_hi + bo, ks > 0 ? 1u : 0u);
+          mma_tf32_ts(d, d + TM_AHI + 8 * ks, b_lo + bo, 1u);
+          mma_tf32_ts(d, d + TM_AHI + 8 * ks, b_hi + bo, 1u);
         }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -225,7 +255,7 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
     }
     for (int i = tid; i < 2 * 64 * STG_LD; i += 128) {
       const int w = i / (64 * STG_LD);
-      reinterpret_cast<float*>(smem + w * ITEM_BYTES + 2 * A_BYTES)[i - w * 64 * STG_LD] = 0.0f;
+      reinterpret_cast<float*>(smem + w * ITEM_BYTES)[i - w * 64 * STG_LD] = 0.0f;
     }
     __syncthreads();
     for (int e = tid; e < p.pat_n; e += 128) {
@@ -240,7 +270,7 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
           const float wk = wts[w][k];
           hx = fmaf(wk, a.x, hx); hy = fmaf(wk, a.y, hy);
         }
-        float* S = reinterpret_cast<float*>(smem + w * ITEM_BYTES + 2 * A_BYTES);
+        float* S = reinterpret_cast<float*>(smem + w * ITEM_BYTES);
         S[r * STG_LD + c] = hx;
         S[(32 + r) * STG_LD + c] = hy;
       }
@@ -261,11 +291,17 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
       }
     };
     // Paterson-Stockmeyer with block 2 (same polynomial as tensorflow_state.py:37-41)
+    auto write_a = [&](const float (&x)[32]) {      // exchange rows with the Re/Im partner, then A row -> TMEM
+      publish_row(sX, rho, x);
+      __syncthreads();
+      write_a_operand(ld_addr, sX, rho, x);
+    };
     if (pp >= 2) {
-      write_operands<true, true>(sA, sB, rho, h);
+      write_a(h);
+      write_b_operand(sB, rho, h);
       product(v, nvalid);                           // v = H^2
       if (dead) break;
-      write_operands<false, true>(sA, sB, rho, v); // H2 as the B operand of every Horner step
+      write_b_operand(sB, rho, v);                  // H2 as the B operand of every Horner step
     }
     int blk;
     if (pp & 1) {
@@ -279,7 +315,7 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
       blk = pp / 2 - 2;
     }
     for (; blk >= 0; --blk) {
-      write_operands<true, false>(sA, sB, rho, r_);
+      write_a(r_);
       product(v, nvalid);                           // v = R * H2
       if (dead) break;
 #pragma unroll
@@ -288,7 +324,8 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
     }
     if (dead) break;
     for (int s = 0; s < p.s; ++s) {                 // squarings (tensorflow_state.py:43-44)
-      write_operands<true, true>(sA, sB, rho, r_);
+      write_a(r_);
+      write_b_operand(sB, rho, r_);
       product(v, nvalid);
       if (dead) break;
 #pragma unroll
@@ -305,14 +342,14 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
   if (dead && tid == 0 && err_flag) atomicExch(err_flag, 1);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(32) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TM_COLS) : "memory");
 }
 
 }  // namespace
 
 cudaError_t qoc_launch_expm_tc32(const QocParams& p, int sm_count, int* err_flag, cudaStream_t st, int64_t* launches) {
   ++*launches;
-  const size_t smem = 2 * ITEM_BYTES + 1024;
+  const size_t smem = SMEM_REQ;
   cudaError_t e = cudaFuncSetAttribute(k_expm_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long pairs = ((long long)p.B * p.T + 1) / 2;

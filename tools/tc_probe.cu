@@ -47,6 +47,14 @@ DEVINL void mma_tf32_mask(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t id
       : "memory");
 }
 
+DEVINL void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 DEVINL void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -73,7 +81,7 @@ __global__ void probe(const float* A /*[2][64][64]*/, const float* B /*[2][64][3
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(32) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(128) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::); }
@@ -90,7 +98,7 @@ __global__ void probe(const float* A /*[2][64][64]*/, const float* B /*[2][64][3
       *reinterpret_cast<float*>(sB + it * 8192 + off) = B[it * 2048 + idx];
     }
   }
-  if (mode == 31 || mode == 32) {
+  if (mode == 31 || mode == 32 || mode == 40) {
     for (int it = 0; it < 2; ++it) {
       for (int idx = tid; idx < 64 * 64; idx += blockDim.x) {
         const int row = idx >> 6, k = idx & 63;
@@ -100,12 +108,12 @@ __global__ void probe(const float* A /*[2][64][64]*/, const float* B /*[2][64][3
       for (int idx = tid; idx < 64 * 32; idx += blockDim.x) {
         const int k = idx >> 5, n = idx & 31;
         uint32_t off = (k >> 3) * 1024 + (k & 7) * 128 + (((n >> 2) ^ (k & 7)) << 4) + (n & 3) * 4;
-        if (mode == 32) off = (k >> 5) * 4096 + (n >> 3) * 1024 + (n & 7) * 128 + ((((k & 31) >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
+        if (mode == 32 || mode == 40) off = (k >> 5) * 4096 + (n >> 3) * 1024 + (n & 7) * 128 + ((((k & 31) >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
         *reinterpret_cast<float*>(sB + it * 8192 + off) = B[it * 2048 + idx];
       }
     }
   }
-  if (mode >= 3 && mode != 31 && mode != 32) for (int i = tid; i < (2 * 16384 + 2 * 8192) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (mode >= 3 && mode != 31 && mode != 32 && mode != 40) for (int i = tid; i < (2 * 16384 + 2 * 8192) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -140,6 +148,18 @@ __global__ void probe(const float* A /*[2][64][64]*/, const float* B /*[2][64][3
     __syncthreads();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (mode == 40) {   // A operand in TMEM: every thread stores its own 64-element row at columns 32..95 of its lane
+    const int it_ = lane >> 4, row_ = 16 * warp + (lane & 15);
+    const uint32_t aaddr = taddr + ((uint32_t)(32 * warp) << 16) + 32;
+    for (int c = 0; c < 64; ++c) {
+      const uint32_t val = __float_as_uint(A[it_ * 4096 + row_ * 64 + c]);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(aaddr + c), "r"(val) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   if (tid == 0 && mode != 1) {
     float chk = 0.f;
     for (int i = 0; i < 64; ++i) chk += reinterpret_cast<float*>(sA)[i * 17] + reinterpret_cast<float*>(sB)[i * 13];
@@ -151,6 +171,11 @@ __global__ void probe(const float* A /*[2][64][64]*/, const float* B /*[2][64][3
         const uint64_t db = make_desc(smem_u32(sB + it * 8192) + ks * 1024, 1024, 128);
         uint64_t da2 = da, db2 = db;
         if (mode == 4) { da2 &= ~((uint64_t)3 << 46); db2 &= ~((uint64_t)3 << 46); }
+        if (mode == 40) {
+          uint64_t b = make_desc(smem_u32(sB + it * 8192) + (ks & 3) * 32 + (ks >> 2) * 4096, 16, 1024) | ((uint64_t)2 << 61);
+          mma_tf32_ts(d, taddr + ((uint32_t)(16 * it) << 16) + 32 + ks * 8, b, IDESC & ~(1u << 16), ks > 0 ? 1u : 0u);
+          continue;
+        }
         if (mode == 32) {   // A and B both K-major SW128
           uint64_t a = make_desc(smem_u32(sA + it * 16384) + (ks & 3) * 32 + (ks >> 2) * 8192, 16, 1024) | ((uint64_t)2 << 61);
           uint64_t b = make_desc(smem_u32(sB + it * 8192) + (ks & 3) * 32 + (ks >> 2) * 4096, 16, 1024) | ((uint64_t)2 << 61);
@@ -202,7 +227,7 @@ __global__ void probe(const float* A /*[2][64][64]*/, const float* B /*[2][64][3
   for (int c = 0; c < 32; ++c) Raw[tid * 32 + c] = __uint_as_float(v[c]);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(32));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(128));
 }
 
 static float tf32_round(float x) {
@@ -217,7 +242,7 @@ int main(int argc, char** argv) {
   srand(1);
   for (auto& x : A) x = tf32_round((rand() / (float)RAND_MAX - 0.5f));
   for (auto& x : B) x = tf32_round((rand() / (float)RAND_MAX - 0.5f));
-  if (mode == 2 || (mode >= 20 && mode != 31 && mode != 32)) { for (auto& x : A) x = 1.f; for (auto& x : B) x = 1.f; }
+  if (mode == 2 || (mode >= 20 && mode != 31 && mode != 32 && mode != 40)) { for (auto& x : A) x = 1.f; for (auto& x : B) x = 1.f; }
   for (int it = 0; it < 2; ++it)
     for (int r = 0; r < 64; ++r)
       for (int c = 0; c < 32; ++c) {
