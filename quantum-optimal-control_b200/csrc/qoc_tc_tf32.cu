@@ -37,7 +37,7 @@ constexpr int NP = 32;
 constexpr uint32_t B_BYTES = 32 * 64 * 4;      // one B-form operand (hi or lo)
 constexpr int XLD = 36;                        // exchange-buffer row stride (floats, 16-byte aligned rows)
 constexpr uint32_t X_BYTES = 64 * XLD * 4;     // row exchange buffer (9 KB)
-constexpr uint32_t ITEM_BYTES = 2 * B_BYTES + 10240;            // B_hi | B_lo | exchange  (26 KB, 1024-aligned)
+constexpr uint32_t ITEM_BYTES = 2 * B_BYTES + 19456;            // B_hi | B_lo | exchange hi rows | exchange lo rows (35 KB, 1024-aligned)
 constexpr int STG_LD = 33;                     // staging row stride (floats)
 constexpr uint32_t TM_COLS = 256;              // TMEM columns per CTA: D [0,32) | A_hi [32,96) | A_lo [96,160)
 constexpr uint32_t TM_AHI = 32, TM_ALO = 96;
@@ -92,13 +92,12 @@ DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-DEVINL void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float d = x - hi;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(d));
-  lo = __uint_as_float(l);
+// x = hi + lo with hi, lo representable in tf32 (10 mantissa bits), both rounded to nearest (ties away)
+// by an integer add on the bit pattern -- 5 instructions; cvt.rna.tf32.f32 expands to ~10 on sm_100a.
+DEVINL void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  const float d = x - __uint_as_float(hi);
+  lo = (__float_as_uint(d) + 0x1000u) & 0xffffe000u;
 }
 
 // byte offset of element (n, k) of a B-form operand (B^T, 32 rows n, K = 64 in two k-blocks)
@@ -116,45 +115,59 @@ DEVINL float4 lds128(uint32_t addr) {
   return v;
 }
 
-// B-form [Xr; Xi]^T (hi and lo) from this thread's stacked row rho (rho < 32: Re row rho, else Im row rho-32)
-DEVINL void write_b_operand(uint32_t sB_hi, int rho, const float (&v)[32]) {
-  const uint32_t sB_lo = sB_hi + B_BYTES;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    float hi, lo;
-    split_tf32(v[c], hi, lo);
-    const uint32_t o = b_off(c, rho);
-    sts32(sB_hi + o, hi);
-    sts32(sB_lo + o, lo);
-  }
+DEVINL void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+DEVINL void sts32u(uint32_t addr, uint32_t a) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory"); }
+DEVINL uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
-// publish this thread's row to the exchange buffer (read by the Re/Im partner thread after a barrier)
-DEVINL void publish_row(uint32_t sX, int rho, const float (&v)[32]) {
-#pragma unroll
-  for (int cc = 0; cc < 8; ++cc) sts128(sX + (rho * XLD + 4 * cc) * 4, v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
-}
-
-// A-form row rho of the embedding [[Xr,-Xi],[Xi,Xr]] into TMEM: columns 0-31 = own row, 32-63 = partner row
-// (negated for Re rows), split into hi (TM_AHI) and lo (TM_ALO) tf32 parts.
-DEVINL void write_a_operand(uint32_t ta_lane, uint32_t sX, int rho, const float (&v)[32]) {
-  const int prow = rho < 32 ? rho + 32 : rho - 32;
-  const float sgn = rho < 32 ? -1.0f : 1.0f;
+// Write the operands derived from this thread's stacked row rho (rho < 32: Re row rho, else Im row rho-32):
+//   WB: B-form [Xr; Xi]^T (hi, lo) into shared memory (scattered 4-byte stores into the K-major swizzled tile);
+//   WA: A-form row rho of [[Xr,-Xi],[Xi,Xr]] into TMEM: columns 0-31 = own row, 32-63 = the Re/Im partner's row
+//       (negated for Re rows), hi part at TM_AHI, lo part at TM_ALO.  The partner's split row comes through the
+//       shared exchange buffer (sX: hi rows, then lo rows); contains one __syncthreads.
+template <bool WA, bool WB>
+DEVINL void write_operands(uint32_t ta_lane, uint32_t sB_hi, uint32_t sX, int rho, int it, const float (&v)[32]) {
   uint32_t hi[32], lo[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) { float h, l; split_tf32(v[c], h, l); hi[c] = __float_as_uint(h); lo[c] = __float_as_uint(l); }
-  tmem_st32(ta_lane + TM_AHI, hi);
-  tmem_st32(ta_lane + TM_ALO, lo);
+  for (int c = 0; c < 32; ++c) split_tf32(v[c], hi[c], lo[c]);
+  if (WB) {
+    const uint32_t sB_lo = sB_hi + B_BYTES;
 #pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {
-    const float4 pv = lds128(sX + (prow * XLD + 4 * cc) * 4);
-    const float x[4] = {sgn * pv.x, sgn * pv.y, sgn * pv.z, sgn * pv.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { float h, l; split_tf32(x[e], h, l); hi[4 * cc + e] = __float_as_uint(h); lo[4 * cc + e] = __float_as_uint(l); }
+    for (int c = 0; c < 32; ++c) {
+      const int cc = c ^ (it << 2);      // the two items of a pair walk the columns in a different order: no bank clash
+      const uint32_t o = b_off(cc, rho);
+      // (the value for column cc is element cc of the row)
+      sts32u(sB_hi + o, it ? hi[c ^ 4] : hi[c]);
+      sts32u(sB_lo + o, it ? lo[c ^ 4] : lo[c]);
+    }
   }
-  tmem_st32(ta_lane + TM_AHI + 32, hi);
-  tmem_st32(ta_lane + TM_ALO + 32, lo);
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  if (WA) {
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      sts128u(sX + (rho * XLD + 4 * cc) * 4, hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+      sts128u(sX + X_BYTES + (rho * XLD + 4 * cc) * 4, lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
+    }
+    tmem_st32(ta_lane + TM_AHI, hi);
+    tmem_st32(ta_lane + TM_ALO, lo);
+    __syncthreads();                     // partner rows are published
+    const int prow = rho < 32 ? rho + 32 : rho - 32;
+    const uint32_t flip = rho < 32 ? 0x80000000u : 0u;      // -Xi for the Re rows
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const uint4 ph = lds128u(sX + (prow * XLD + 4 * cc) * 4);
+      const uint4 pl = lds128u(sX + X_BYTES + (prow * XLD + 4 * cc) * 4);
+      hi[4 * cc] = ph.x ^ flip; hi[4 * cc + 1] = ph.y ^ flip; hi[4 * cc + 2] = ph.z ^ flip; hi[4 * cc + 3] = ph.w ^ flip;
+      lo[4 * cc] = pl.x ^ flip; lo[4 * cc + 1] = pl.y ^ flip; lo[4 * cc + 2] = pl.z ^ flip; lo[4 * cc + 3] = pl.w ^ flip;
+    }
+    tmem_st32(ta_lane + TM_AHI + 32, hi);
+    tmem_st32(ta_lane + TM_ALO + 32, lo);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
 }
 
 __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag) {
@@ -291,17 +304,11 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
       }
     };
     // Paterson-Stockmeyer with block 2 (same polynomial as tensorflow_state.py:37-41)
-    auto write_a = [&](const float (&x)[32]) {      // exchange rows with the Re/Im partner, then A row -> TMEM
-      publish_row(sX, rho, x);
-      __syncthreads();
-      write_a_operand(ld_addr, sX, rho, x);
-    };
     if (pp >= 2) {
-      write_a(h);
-      write_b_operand(sB, rho, h);
+      write_operands<true, true>(ld_addr, sB, sX, rho, it, h);
       product(v, nvalid);                           // v = H^2
       if (dead) break;
-      write_b_operand(sB, rho, v);                  // H2 as the B operand of every Horner step
+      write_operands<false, true>(ld_addr, sB, sX, rho, it, v);    // H2 as the B operand of every Horner step
     }
     int blk;
     if (pp & 1) {
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
       blk = pp / 2 - 2;
     }
     for (; blk >= 0; --blk) {
-      write_a(r_);
+      write_operands<true, false>(ld_addr, sB, sX, rho, it, r_);
       product(v, nvalid);                           // v = R * H2
       if (dead) break;
 #pragma unroll
@@ -324,8 +331,7 @@ __global__ void __launch_bounds__(128, 2) k_expm_tc32(QocParams p, int* err_flag
     }
     if (dead) break;
     for (int s = 0; s < p.s; ++s) {                 // squarings (tensorflow_state.py:43-44)
-      write_a(r_);
-      write_b_operand(sB, rho, r_);
+      write_operands<true, true>(ld_addr, sB, sX, rho, it, r_);
       product(v, nvalid);
       if (dead) break;
 #pragma unroll
