@@ -303,8 +303,17 @@ def run_ours(args):
     else:
         taylor_equiv = ps_products
     executed = 8.0 * np_pad ** 3 * (taylor_equiv + s) * T * B * (3 if args.dtype == "tf32x3" else 1)
-    roof = {"kernel": "k_expm_tc32 (tcgen05)" if args.dtype == "tf32x3" else "k_expm_mma (DMMA)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+    kname = "k_expm_tc32 (tcgen05)" if args.dtype == "tf32x3" else "k_expm_mma (DMMA)"
+    traffic = None                       # dram bytes per launch from the committed ncu capture (same workload only)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kname)
+        if tr and args.workload == "C2" and args.steps_T is None and args.batch is None:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:  # noqa: BLE001
+        pass
+    roof = {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic,
+            "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
             "peak_source": peak_src,
             "pipe": ("tf32 tensor pipe via tcgen05 (3 MMAs per product: 3xTF32 operand split)" if args.dtype == "tf32x3"
                      else "fp64 (tcgen05 has no f64 kind; bound is the FP64 FMA/DMMA pipe)"),
