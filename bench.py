@@ -250,6 +250,7 @@ def run_ours(args):
     value = B * world * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))      # host Adam: share the cores between ranks
     hbase = eng.host_buffers()['base']                      # pinned host weights, updated in place by the host Adam
     hbase[...] = np.asarray(sp.ops_weight_base, dtype=np.float64)
     hadam = HostAdam(hbase.shape)
