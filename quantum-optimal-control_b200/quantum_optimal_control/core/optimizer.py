@@ -72,7 +72,7 @@ class run_session:
     """Same constructor shape and result attributes (``uks``, ``Uf``) as the reference class."""
 
     def __init__(self, engine, conv, sys_para, method, show_plots=True, single_simulation=False, use_gpu=True,
-                 quiet=False):
+                 quiet=False, run_file=None):
         import torch
         self.torch = torch
         self.engine = engine
@@ -83,6 +83,8 @@ class run_session:
         self.method = method.upper()
         self.show_plots = show_plots
         self.quiet = quiet
+        self.run_file = run_file
+        self.elapsed = 0.0
         self.B = engine.B
         sp = sys_para
         base0 = np.asarray(sp.ops_weight_base, dtype=np.float64).reshape(self.B, sp.ops_len, sp.steps)
@@ -129,25 +131,80 @@ class run_session:
             adam.step(self.base, out['grad'], lr, frozen=done if self.B > 1 else None)        # :67-69
 
     def update_and_save(self):
-        """core/run_session.py:75-92 (console line only; HDF5/plots are optional host code)."""
+        """core/run_session.py:75-92: every update_step a summary save + console line, every evol_save_step the
+        final state and the state trajectories (plots are out of scope; show_plots only silences the console)."""
         if not self.end:
             if self.iterations % self.conv.update_step == 0:
+                self.save_data()
                 self.display()
+            if self.iterations % self.conv.evol_save_step == 0:
+                if not (self.sys_para.show_plots and self.iterations % self.conv.update_step == 0):
+                    if self.iterations % self.conv.update_step != 0:
+                        self.save_data()
+                    self.save_evol()
             self.iterations += 1
+
+    def _uks_now(self):
+        w = self.torch.sin(self.base).cpu().numpy()
+        uks = np.asarray(self.sys_para.ops_max_amp)[None, :, None] * w
+        return uks if self.sys_para.batched else uks[0]
+
+    def _pick(self, x):
+        x = np.asarray(x)
+        return x if self.sys_para.batched else x[0]
+
+    def save_data(self):
+        """core/run_session.py:129-138."""
+        if self.run_file is None:
+            return
+        self.elapsed = time.time() - self.start_time
+        rf = self.run_file
+        rf.append('error', self._pick(self.l))
+        rf.append('reg_error', self._pick(self.rl))
+        rf.append('uks', self._uks_now())
+        rf.append('iteration', np.array(self.iterations))
+        rf.append('run_time', np.array(self.elapsed))
+        rf.append('unitary_scale', self._pick(self.metric))
+
+    def save_evol(self, ev=None):
+        """Convergence.save_evol -> Analysis.get_final_state / get_inter_vecs (core/analysis.py:26-35,44-101)."""
+        if self.run_file is None:
+            return
+        from ..helper_functions.grape_functions import c_to_r_mat, sort_ev
+        sp, rf = self.sys_para, self.run_file
+        if ev is None:
+            ev = self.engine.evolve(self.base, want_inter_vecs=sp.use_inter_vecs)
+        if not sp.state_transfer:
+            U = ev['U_final'].cpu().numpy()
+            rf.append('final_state', self._pick(np.stack([c_to_r_mat(u) for u in U])))
+        if sp.use_inter_vecs and ev['inter_vecs'] is not None:
+            iv = np.transpose(ev['inter_vecs'].cpu().numpy(), (0, 2, 3, 1))        # [B, m, n, T+1]
+            rf.append('inter_vecs_raw_real', self._pick(iv.real))
+            rf.append('inter_vecs_raw_imag', self._pick(iv.imag))
+            if sp.is_dressed:                                                         # analysis.py:76-84 (plain transpose)
+                vt = np.transpose(sort_ev(sp.v_c, sp.dressed_id))
+                iv = np.einsum('ac,bjct->bjat', vt, iv)
+            rf.append('inter_vecs_mag_squared', self._pick(np.abs(iv) ** 2))
+            rf.append('inter_vecs_real', self._pick(iv.real))
+            rf.append('inter_vecs_imag', self._pick(iv.imag))
 
     def display(self):
         if self.quiet:
             return
         b = int(np.argmin(self.l))
-        self.elapsed = time.time() - self.start_time
+        if self.run_file is None:
+            self.elapsed = time.time() - self.start_time        # the reference only sets it in save_data (run_session.py:131)
         print('Error = :%1.2e; Runtime: %.1fs; Iterations = %d, grads =  %10.3e, unitary_metric = %.5f' % (
             self.l[b], self.elapsed, self.iterations, self.g_squared[b], self.metric[b]))
 
     def get_end_results(self):
         """core/run_session.py:94-117 + core/analysis.py:18-41."""
         sp = self.sys_para
+        self.save_data()
         self.display()
         ev = self.engine.evolve(self.base, want_inter_vecs=sp.use_inter_vecs)
+        if not self.show_plots:
+            self.save_evol(ev)                                          # run_session.py:103-104
         w = self.torch.sin(self.base).cpu().numpy()                     # Analysis.get_ops_weight
         uks = np.asarray(sp.ops_max_amp)[None, :, None] * w             # Get_uks
         Uf = ev['U_final'].cpu().numpy()
@@ -157,6 +214,9 @@ class run_session:
             self.uks, self.Uf = uks, Uf
         else:
             self.uks, self.Uf = uks[0], Uf[0]
+        if self.run_file is not None and not sp.state_transfer:        # get_final_state() appends once more (:107)
+            from ..helper_functions.grape_functions import c_to_r_mat
+            self.run_file.append('final_state', self._pick(np.stack([c_to_r_mat(u) for u in Uf])))
         if sp.state_transfer:
             self.Uf = []
 

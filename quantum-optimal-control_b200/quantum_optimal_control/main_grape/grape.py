@@ -37,16 +37,17 @@ def Grape(H0, Hops, Hnames, U, total_time, steps, states_concerned_list, converg
     if convergence is None:                                                         # grape.py:91-92
         convergence = {'rate': 0.01, 'update_step': 100, 'max_iterations': 5000, 'conv_target': 1e-8,
                        'learning_rate_decay': 2500}
-    file_path = None
+    file_path, run_file = None, None
     if save:                                                                        # grape.py:36-87
         if file_name is None:
             raise ValueError('Grape function input: file_name, is not specified.')
         if data_path is None:
             raise ValueError('Grape function input: data_path, is not specified.')
         file_path = storage.new_run_file(data_path, file_name)
+        run_file = storage.RunFile(file_path)
         if not quiet:
             print("data saved at: " + str(file_path))
-        storage.save_inputs(file_path, dict(H0=H0, Hops=Hops, Hnames=Hnames, U=U, total_time=total_time, steps=steps,
+        storage.save_inputs(run_file, dict(H0=H0, Hops=Hops, Hnames=Hnames, U=U, total_time=total_time, steps=steps,
                                             states_concerned_list=states_concerned_list, use_gpu=use_gpu,
                                             sparse_H=sparse_H, sparse_U=sparse_U, sparse_K=sparse_K, maxA=maxA,
                                             initial_guess=initial_guess, method=method),
@@ -64,12 +65,17 @@ def Grape(H0, Hops, Hnames, U, total_time, steps, states_concerned_list, converg
                                 maxAmp, draw, initial_guess, show_plots, unitary_error, state_transfer, no_scaling,
                                 reg_coeffs, save, file_path, Taylor_terms, use_gpu, use_inter_vecs, sparse_H,
                                 sparse_U, sparse_K, batch=batch)
+    if save:                                                                        # system_parameters.py:189-191,233-236
+        run_file.add('initial_vectors_c', np.array(sys_para.initial_vectors_c))
+        run_file.add('taylor_terms', sys_para.exp_terms)
+        run_file.add('taylor_scaling', sys_para.scaling)
     engine = GrapeEngine.from_sys_para(sys_para, dtype=dtype, device=device)
     conv = Convergence(sys_para, time_unit, convergence)
     try:
-        SS = run_session(engine, conv, sys_para, method, show_plots=sys_para.show_plots, use_gpu=use_gpu, quiet=quiet)
+        SS = run_session(engine, conv, sys_para, method, show_plots=sys_para.show_plots, use_gpu=use_gpu, quiet=quiet,
+                         run_file=run_file)
         if save:
-            storage.save_results(file_path, SS, sys_para, time.time() - grape_start_time)
+            run_file.add('wall_clock_time', np.array(time.time() - grape_start_time))     # grape.py:123-127
             if not quiet:
                 print("data saved at: " + str(file_path))
         if return_losses:
@@ -77,7 +83,7 @@ def Grape(H0, Hops, Hnames, U, total_time, steps, states_concerned_list, converg
         return SS.uks, SS.Uf
     except KeyboardInterrupt:                                                       # grape.py:130-139
         if save:
-            storage.save_scalar(file_path, 'wall_clock_time', time.time() - grape_start_time)
+            run_file.add('wall_clock_time', np.array(time.time() - grape_start_time))
         return None
     finally:
         engine.close()

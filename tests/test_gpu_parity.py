@@ -413,3 +413,36 @@ def test_population_sweep_two_gpus_nccl(built_lib, tmp_path):
     uks, Uf, losses = Grape(*args, initial_guess=g, convergence=conv, save=False, show_plots=False, quiet=True, return_losses=True, **kw)
     assert np.allclose(res['loss'], losses, atol=1e-12) and int(res['best']) == int(np.argmin(losses))
     assert np.allclose(res['uks'], uks[int(res['best'])], atol=1e-12)
+
+
+def test_run_file_schema(built_lib, tmp_path):
+    """save=True writes the reference's datasets (core/run_session.py:129-138, core/analysis.py:31-33,62-65,95-99)."""
+    import os
+    from quantum_optimal_control.main_grape.grape import Grape
+    pb = W.c1_pi_pulse(T=20)
+    args, kw = W.grape_kwargs(pb)
+    guess = W.random_guess(2, 20, pb['maxA'], 2)
+    conv = {'rate': 0.02, 'update_step': 4, 'evol_save_step': 4, 'max_iterations': 9, 'conv_target': 1e-12,
+            'learning_rate_decay': 100}
+    uks, Uf = Grape(*args, convergence=conv, initial_guess=guess, save=True, file_name="run", data_path=str(tmp_path),
+                    show_plots=False, quiet=True, **kw)
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].startswith("00000_run")
+    path = str(tmp_path / files[0])
+    if path.endswith(".npz"):
+        f = dict(np.load(path, allow_pickle=True))
+    else:
+        import h5py
+        with h5py.File(path, 'r') as hf:
+            f = {}
+            hf.visititems(lambda k, v: f.__setitem__(k, v[()]) if hasattr(v, 'shape') else None)
+    n_saves = 3 + 1                     # iterations 0, 4, 8 and the end result
+    assert f['error'].shape == (n_saves,) and f['uks'].shape == (n_saves, 2, 20)
+    assert list(f['iteration']) == [0, 4, 8, 9]
+    assert np.allclose(f['uks'][-1], uks)
+    assert f['final_state'].shape == (n_saves + 1, 4, 4)          # the end result appends it twice, like the reference
+    fs = f['final_state'][-1]
+    assert np.allclose(fs[:2, :2] + 1j * fs[2:, :2], Uf)
+    assert f['inter_vecs_raw_real'].shape == (n_saves, 2, 2, 21) and f['inter_vecs_mag_squared'].shape == (n_saves, 2, 2, 21)
+    assert int(f['taylor_terms']) == 7 and int(f['taylor_scaling']) == 2 and 'wall_clock_time' in f
+    assert f['convergence/max_iterations'] == 9 and np.allclose(f['H0'], pb['H0'])

@@ -146,10 +146,18 @@ def test_reg_struct_and_storage(tmp_path):
     with pytest.raises(ValueError):
         reg_struct({'bandpass': 1.0}, 5, 10)
     p1 = storage.new_run_file(str(tmp_path), "run")
-    storage.save_inputs(p1, dict(H0=np.eye(2), steps=5, maxA=None), {'rate': 0.1}, {'dwdt': 1.0}, None)
-    storage.save_scalar(p1, 'wall_clock_time', 1.5)
+    rf = storage.RunFile(p1)
+    storage.save_inputs(rf, dict(H0=np.eye(2), steps=5, maxA=None), {'rate': 0.1}, {'dwdt': 1.0}, None)
+    rf.add('wall_clock_time', 1.5)
+    for it in range(3):                                         # H5File.append semantics: a new leading axis per save
+        rf.append('error', np.array(0.5 / (it + 1)))
+        rf.append('uks', np.full((2, 4), float(it)))
     p2 = storage.new_run_file(str(tmp_path), "run")
     assert os.path.basename(p1).startswith("00000_run") and os.path.basename(p2).startswith("00001_run")
+    if p1.endswith(".npz"):
+        with np.load(p1, allow_pickle=True) as f:
+            assert f['error'].shape == (3,) and f['uks'].shape == (3, 2, 4) and f['uks'][2, 0, 0] == 2.0
+            assert float(f['convergence/rate']) == 0.1 and float(f['reg_coeffs/dwdt']) == 1.0 and 'maxA' not in f.files
 
 
 _GLOO = r'''
