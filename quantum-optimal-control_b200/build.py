@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libqoc_b200.so")
-SOURCES = ["qoc_mma_f64.cu", "qoc_large_f64.cu", "qoc_tc_tf32.cu", "qoc_sweeps.cu", "qoc_api.cu"]
+SOURCES = ["qoc_mma_f64.cu", "qoc_large_f64.cu", "qoc_tc_tf32.cu", "qoc_sweeps.cu", "qoc_vecsweep.cu", "qoc_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -37,6 +37,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("QOC_NVCC_EXTRA", "").split()          # e.g. -DQOC_CMUL_3M=0 for A/B runs
     objs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))

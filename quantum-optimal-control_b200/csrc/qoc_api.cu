@@ -15,7 +15,7 @@ static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 static int pick_np(int n) { return n <= 64 ? (n + 7) / 8 * 8 : -1; }
 
-struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, scratch, total; };
+struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, seg, scratch, total; };
 
 static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
   // Bc = instances processed per pass (batch chunk); P / psi / lam / gctrl / ot / scratch are reused by every pass
@@ -34,6 +34,9 @@ static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
   L.st_base = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_grad = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_out = off; off += align_up((size_t)d.B * 4 * sizeof(double));
+  L.seg = off;                                   // segment products of the re-associated U_final chain (n <= 64, fp64)
+  if (d.n <= 64 && d.dtype == QOC_F64)
+    off += align_up((size_t)Bc * ((d.T + QOC_SEG_LEN - 1) / QOC_SEG_LEN) * nn * sizeof(cplx));
   L.scratch = off;
   if (d.n > 64) off += align_up(qoc_large_scratch_elems(d.n, Bc, sm_count) * sizeof(cplx));
   L.total = off;
@@ -70,6 +73,7 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   h->sm_count = 0;
   h->profiling = false; h->ev_recorded = 0;
   for (int i = 0; i <= QOC_NUM_KERNELS; ++i) h->ev[i] = nullptr;
+  h->hi = nullptr; h->ev_fork = h->ev_join = nullptr; h->hi_pending = false; h->work = nullptr; h->seg = nullptr;
   *out = h;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -105,6 +109,15 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   if (cudaMalloc((void**)&h->err_flag, sizeof(int)) != cudaSuccess || cudaMemset(h->err_flag, 0, sizeof(int)) != cudaSuccess) {
     h->err = "cudaMalloc failed"; return QOC_ECUDA;
   }
+  {   // high-priority stream for the loss / gradient critical path; the U_final branch stays on the caller's stream
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      h->err = "cannot create the high-priority stream"; return QOC_ECUDA;
+    }
+  }
   return QOC_OK;
 }
 
@@ -114,6 +127,9 @@ int qoc_destroy(qoc_handle_t h) {
   cudaFree(h->cidx); cudaFree(h->coo_off); cudaFree(h->coo_r); cudaFree(h->coo_c);
   cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw); cudaFree(h->dressW); cudaFree(h->psid); cudaFree(h->pat_rc); cudaFree(h->pat_coef); cudaFree(h->pat_coef_f); cudaFree(h->err_flag);
   for (int i = 0; i <= QOC_NUM_KERNELS; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->hi) { cudaStreamSynchronize(h->hi); cudaStreamDestroy(h->hi); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return QOC_OK;
 }
@@ -139,6 +155,7 @@ int qoc_set_workspace(qoc_handle_t h, void* dev_ptr, size_t bytes) {
   h->gctrl = (double*)(w + L.gctrl); h->ot = (cplx*)(w + L.ot); h->scal = (double*)(w + L.scal);
   h->Ufin = (cplx*)(w + L.Ufin);
   h->st_base = (double*)(w + L.st_base); h->st_grad = (double*)(w + L.st_grad); h->st_out = (double*)(w + L.st_out);
+  h->seg = (cplx*)(w + L.seg);
   h->scratch = w + L.scratch;
   h->ws_set = true;
   return QOC_OK;
@@ -316,9 +333,47 @@ static QocParams chunk_params(const QocParams& p, const qoc_dims_t& d, int b0, i
   return q;
 }
 
+// Few concerned states (m < NP/2) on the fp64 shared-memory path: the loss and the gradient only need
+// the m state columns, which k_vec_sweep propagates (HBM-bound) on the handle's high-priority stream;
+// the full n x n product -- U_final / unitary_scale, wanted by the caller but by nothing downstream --
+// is re-associated into segment products (k_segprod) + a short chain and runs on the caller's stream
+// beside it.  QOC_B200_NO_VEC_SWEEP=1 restores the single-stream chain.
+static bool use_vec_sweeps(qoc_handle_t h, const QocParams& p) {
+  static const bool off = getenv("QOC_B200_NO_VEC_SWEEP") != nullptr;
+  return !off && h->d.dtype == QOC_F64 && h->d.n <= 64 && 2 * h->d.m < h->NP && qoc_vec_sweep_supported(p);
+}
+
+// the caller's stream waits for the critical-path branch
+static int join_hi(qoc_handle_t h, cudaStream_t st) {
+  if (!h->hi_pending) return QOC_OK;
+  h->hi_pending = false;
+  CUDA_TRY(h, cudaEventRecord(h->ev_join, h->hi));
+  CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+  h->work = st;
+  return QOC_OK;
+}
+
+// U_final / unitary_scale without the states: segment products + chain over the segments (T >= 4 segments),
+// else the plain chain
+static int launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
+  QocParams q = p;
+  q.chain_no_psi = 1;
+  const int L = QOC_SEG_LEN, S = (p.T + L - 1) / L;
+  if (S >= 4) {
+    CUDA_TRY(h, qoc_launch_segprod_f64(p, h->NP, L, S, h->seg, st, &h->launches));
+    q.P = h->seg; q.T = S;
+  }
+  CUDA_TRY(h, qoc_launch_chain_f64(q, h->NP, 0, st, &h->launches));
+  return QOC_OK;
+}
+
+// Forward pass.  On return h->work is the stream the caller must use for everything that consumes psi
+// (fwd_reduce has run on it); join_hi() brings the caller's stream back in.
 static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   int rc;
   h->ev_recorded = 0;
+  if ((rc = join_hi(h, st))) return rc;
+  h->work = st;
   if ((rc = prof_mark(h, 0, st))) return rc;
   const bool large = h->d.n > 64;                   // matrices do not fit in shared memory: tiled global-operand path
   if (h->d.dtype == QOC_TF32X3) CUDA_TRY(h, qoc_launch_expm_tc32(p, h->sm_count, h->err_flag, st, &h->launches));
@@ -326,11 +381,22 @@ static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   else CUDA_TRY(h, qoc_launch_expm_f64(p, h->NP, h->sm_count, st, &h->launches));
   if ((rc = prof_mark(h, 1, st))) return rc;
   if (large) CUDA_TRY(h, qoc_launch_chain_large(p, h->scratch, st, &h->launches));
-  else CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, h->d.dtype != QOC_F64, st, &h->launches));
-  if ((rc = prof_mark(h, 2, st))) return rc;
-  if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 0, st, &h->launches));
-  CUDA_TRY(h, qoc_launch_fwd_reduce(p, st, &h->launches));
-  if ((rc = prof_mark(h, 3, st))) return rc;
+  else if (use_vec_sweeps(h, p)) {
+    static const int xmode = getenv("QOC_B200_XCHAIN") ? atoi(getenv("QOC_B200_XCHAIN")) : 2;   // debug: 0 skip, 1 serial
+    if (xmode == 2) {
+      CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));                    // both branches start when the propagators are done
+      CUDA_TRY(h, cudaStreamWaitEvent(h->hi, h->ev_fork, 0));
+      h->work = h->hi;
+      h->hi_pending = true;
+    }
+    CUDA_TRY(h, qoc_launch_vec_sweep(p, 0, h->work, &h->launches));   // critical path first: psi(t)
+    if (!p.state_transfer && xmode != 0 && (rc = launch_xchain(h, p, st))) return rc;
+  } else CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, h->d.dtype != QOC_F64, st, &h->launches));
+  cudaStream_t ws = h->work;
+  if ((rc = prof_mark(h, 2, ws))) return rc;
+  if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 0, ws, &h->launches));
+  CUDA_TRY(h, qoc_launch_fwd_reduce(p, ws, &h->launches));
+  if ((rc = prof_mark(h, 3, ws))) return rc;
   return QOC_OK;
 }
 
@@ -349,17 +415,20 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
     p = chunk_params(full, h->d, b0, h->d.B - b0 < h->Bc ? h->d.B - b0 : h->Bc);
     rc = run_forward(h, p, st);
     if (rc) return rc;
-    if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 1, st, &h->launches));
+    cudaStream_t ws = h->work;
+    if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 1, ws, &h->launches));
     // dense-m problems (m >= NP/2, dense controls) take the DMMA costate / gradient kernels
     const bool dense_m = h->d.n <= 64 && h->d.dtype == QOC_F64 && 2 * h->d.m >= h->NP && h->d.m <= h->NP;
     const bool dense_A = (double)h->nnz >= 0.25 * (double)h->d.K * h->d.n * h->d.n;
-    if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, st, &h->launches));
-    else if (dense_m) CUDA_TRY(h, qoc_launch_costate_mma(p, h->NP, st, &h->launches));
-    else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, st, &h->launches));
-    if ((rc = prof_mark(h, 4, st))) return rc;
-    if (dense_m && dense_A) CUDA_TRY(h, qoc_launch_grad_mma(p, h->NP, h->sm_count, st, &h->launches));
-    else CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, st, &h->launches));
-    if ((rc = prof_mark(h, 5, st))) return rc;
+    if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, ws, &h->launches));
+    else if (dense_m) CUDA_TRY(h, qoc_launch_costate_mma(p, h->NP, ws, &h->launches));
+    else if (use_vec_sweeps(h, p)) CUDA_TRY(h, qoc_launch_vec_sweep(p, 1, ws, &h->launches));
+    else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, ws, &h->launches));
+    if ((rc = prof_mark(h, 4, ws))) return rc;
+    if (dense_m && dense_A) CUDA_TRY(h, qoc_launch_grad_mma(p, h->NP, h->sm_count, ws, &h->launches));
+    else CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, ws, &h->launches));
+    if ((rc = prof_mark(h, 5, ws))) return rc;
+    if ((rc = join_hi(h, st))) return rc;                  // finalize reads both branches; the next pass rewrites P
     CUDA_TRY(h, qoc_launch_finalize(p, st, &h->launches));
     if ((rc = prof_mark(h, 6, st))) return rc;
   }
@@ -380,6 +449,7 @@ int qoc_evolve(qoc_handle_t h, const double* base_dev, double* U_final_dev, doub
     p = chunk_params(full, d, b0, bc);
     rc = run_forward(h, p, st);
     if (rc) return rc;
+    if ((rc = join_hi(h, st))) return rc;
     if (inter_vecs_dev) {
       const size_t per = (size_t)(d.T + 1) * d.m * d.n * 2;      // doubles per instance
       CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_dev + (size_t)b0 * per, h->psi, (size_t)bc * per * sizeof(double),
@@ -447,6 +517,7 @@ int qoc_evolve_host(qoc_handle_t h, const double* base_host, double* U_final_hos
       p = chunk_params(full, d, b0, bc);
       rc = run_forward(h, p, st);
       if (rc) return rc;
+      if ((rc = join_hi(h, st))) return rc;
       CUDA_TRY(h, cudaMemcpyAsync(inter_vecs_host + (size_t)b0 * per, h->psi, (size_t)bc * per * sizeof(double),
                                   cudaMemcpyDeviceToHost, st));
     }

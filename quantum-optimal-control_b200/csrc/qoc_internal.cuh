@@ -7,12 +7,15 @@
 
 typedef double2 cplx;
 
+#define QOC_SEG_LEN 16   // propagators per segment product (k_segprod)
+
 // Everything the kernels need, passed by value.
 struct QocParams {
   int n, K, T, m, B, p, s;
   int has_cidx;
   int state_transfer;
   int herm;             // every generator A_k is anti-Hermitian (Hermitian Hamiltonians)
+  int chain_no_psi;     // k_chain_mma only propagates X (U_final, unitary_scale); psi comes from k_vec_sweep
   double dt, inv2s;
   double invfact[32];   // 1/j!
   // constants
@@ -74,12 +77,20 @@ struct qoc_handle_s {
   void* scratch;                          // n > 64: per-CTA global intermediates
   int64_t launches;
   bool profiling; int ev_recorded;
+  cudaStream_t hi;                        // high-priority stream of the loss / gradient critical path (vec-sweep mode)
+  cudaEvent_t ev_fork, ev_join;
+  bool hi_pending;
+  cudaStream_t work;                      // where the current pass's sweep / gradient kernels go (hi or the caller's stream)
+  cplx* seg;                              // [Bc][ceil(T/QOC_SEG_LEN)][n][n] segment products
   cudaEvent_t ev[QOC_NUM_KERNELS + 1];
 };
 
 // kernel launchers (qoc_mma_f64.cu, qoc_sweeps.cu); return cudaError_t, bump *launches
 cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_segprod_f64(const QocParams& p, int NP, int L, int S, cplx* seg_out, cudaStream_t st, int64_t* launches);
+bool qoc_vec_sweep_supported(const QocParams& p);
+cudaError_t qoc_launch_vec_sweep(const QocParams& p, int reverse, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_expm_tc32(const QocParams& p, int sm_count, int* err_flag, cudaStream_t st, int64_t* launches);
 size_t qoc_large_scratch_elems(int n, int B, int sm_count);
 cudaError_t qoc_launch_expm_large(const QocParams& p, int sm_count, void* scratch, cudaStream_t st, int64_t* launches);

@@ -47,6 +47,13 @@ DEVINL void dmma(double& d0, double& d1, const double a, const double b) {
                : "d"(a), "d"(b));
 }
 
+// program-ordered fp64 add (operand sums of the 3M product are scheduled by hand, see mma_gemm)
+DEVINL double dadd_v(const double a, const double b) {
+  double r;
+  asm volatile("add.f64 %0, %1, %2;\n" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+
 template <int NP, int RB, int CB>
 struct MT {
   static constexpr int NBLK = NP / 8;
@@ -60,20 +67,83 @@ struct MT {
 
 // Complex C = A * B on swizzled shared operands; the warp owns block rows [rb0, rb0+RB) and block
 // columns [cb0, cb0+CB).  cr/ci[i][j][e] = Re/Im C[8(rb0+i)+g][8(cb0+j)+2q+e].
+// 3M (Gauss) complex product: with t1 = Ar Br, t2 = Ai Bi, t3 = (Ar+Ai)(Br+Bi),
+//   Re C = t1 - t2,  Im C = t3 - t1 - t2   -> 3 real DMMAs per 8x8x4 block instead of 4.
+// The operand sums cost one DADD per loaded fragment element (RB + CB per k-step against
+// 3 RB CB DMMAs); the result differs from the 4-product form by O(eps |A||B|) (normwise stable).
+// QOC_CMUL_3M=0 restores the 4-product form.
+#ifndef QOC_CMUL_3M
+#define QOC_CMUL_3M 1
+#endif
+
 template <int NP, int RB, int CB>
 DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, double (&cr)[RB][CB][2],
                      double (&ci)[RB][CB][2], int rb0, int cb0, int ksteps, int lane) {
   const int g = lane >> 2, q = lane & 3;
   int arow[RB], amask[RB];
+#if QOC_CMUL_3M
+  double t2[RB][CB][2];
+#endif
 #pragma unroll
   for (int i = 0; i < RB; ++i) {
     const int r = 8 * (rb0 + i) + g;
     arow[i] = r * NP;
     amask[i] = sw_mask(r);
 #pragma unroll
-    for (int j = 0; j < CB; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+    for (int j = 0; j < CB; ++j) {
+      cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+#if QOC_CMUL_3M
+      t2[i][j][0] = t2[i][j][1] = 0.0;
+#endif
+    }
   }
   const int bc = 8 * cb0 + g;
+#if QOC_CMUL_3M
+  // software-pipelined by one k-step: the fragments and operand sums of step ks+1 are produced
+  // while the DMMAs of step ks issue, so no DMMA ever waits on a just-issued LDS or DADD
+  cplx a[RB], b[CB];
+  double sa[RB], sb[CB];
+  {
+    const int k = q;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) a[i] = A[arow[i] + (k ^ amask[i])];
+    const int bm = sw_mask(k);
+#pragma unroll
+    for (int j = 0; j < CB; ++j) b[j] = B[k * NP + ((bc + 8 * j) ^ bm)];
+  }
+#pragma unroll
+  for (int i = 0; i < RB; ++i) sa[i] = dadd_v(a[i].x, a[i].y);
+#pragma unroll
+  for (int j = 0; j < CB; ++j) sb[j] = dadd_v(b[j].x, b[j].y);
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ++ks) {
+    cplx an[RB], bn[CB];
+    {                                           // fragments of the next k-step (the last step re-reads its own)
+      const int k = 4 * min(ks + 1, ksteps - 1) + q;
+#pragma unroll
+      for (int i = 0; i < RB; ++i) an[i] = A[arow[i] + (k ^ amask[i])];
+      const int bm = sw_mask(k);
+#pragma unroll
+      for (int j = 0; j < CB; ++j) bn[j] = B[k * NP + ((bc + 8 * j) ^ bm)];
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(t2[i][j][0], t2[i][j][1], a[i].y, b[j].y);
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], sa[i], sb[j]);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) { a[i] = an[i]; sa[i] = dadd_v(an[i].x, an[i].y); }
+#pragma unroll
+    for (int j = 0; j < CB; ++j) { b[j] = bn[j]; sb[j] = dadd_v(bn[j].x, bn[j].y); }
+  }
+#else
 #pragma unroll 2
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k = 4 * ks + q;
@@ -103,6 +173,19 @@ DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
 #pragma unroll
       for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
   }
+#endif
+#if QOC_CMUL_3M
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < CB; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double t1 = cr[i][j][e], u = t2[i][j][e];
+        cr[i][j][e] = t1 - u;
+        ci[i][j][e] = ci[i][j][e] - t1 - u;
+      }
+#endif
 }
 
 template <int NP, int RB, int CB>
@@ -152,8 +235,54 @@ DEVINL void tri_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
   const int g = lane >> 2, q = lane & 3;
   const int ra = 8 * H_::RA + g, rb = 8 * H_::RB_ + g;
   const int ma = sw_mask(ra), mb = sw_mask(rb);
+#if QOC_CMUL_3M
+  double t2[H_::NB][2];
+#pragma unroll
+  for (int b = 0; b < H_::NB; ++b) t2[b][0] = t2[b][1] = 0.0;
+#endif
 #pragma unroll
   for (int b = 0; b < H_::NB; ++b) cr[b][0] = cr[b][1] = ci[b][0] = ci[b][1] = 0.0;
+#if QOC_CMUL_3M
+  cplx a0, a1, bv[H_::CA];                     // bv: columns RA..NBLK-1 (superset of RB_..NBLK-1)
+  double s0, s1, sb[H_::CA];
+  {
+    const int k = q, bm = sw_mask(k);
+    a0 = A[ra * NP + (k ^ ma)];
+    a1 = A[rb * NP + (k ^ mb)];
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) bv[j] = B[k * NP + ((8 * (H_::RA + j) + g) ^ bm)];
+  }
+  s0 = dadd_v(a0.x, a0.y); s1 = dadd_v(a1.x, a1.y);
+#pragma unroll
+  for (int j = 0; j < H_::CA; ++j) sb[j] = dadd_v(bv[j].x, bv[j].y);
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ++ks) {
+    cplx a0n, a1n, bn[H_::CA];
+    {
+      const int k = 4 * min(ks + 1, ksteps - 1) + q, bm = sw_mask(k);
+      a0n = A[ra * NP + (k ^ ma)];
+      a1n = A[rb * NP + (k ^ mb)];
+#pragma unroll
+      for (int j = 0; j < H_::CA; ++j) bn[j] = B[k * NP + ((8 * (H_::RA + j) + g) ^ bm)];
+    }
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) dmma(cr[j][0], cr[j][1], a0.x, bv[j].x);
+#pragma unroll
+    for (int j = 0; j < H_::CB_; ++j) dmma(cr[H_::CA + j][0], cr[H_::CA + j][1], a1.x, bv[H_::RB_ - H_::RA + j].x);
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) dmma(t2[j][0], t2[j][1], a0.y, bv[j].y);
+#pragma unroll
+    for (int j = 0; j < H_::CB_; ++j) dmma(t2[H_::CA + j][0], t2[H_::CA + j][1], a1.y, bv[H_::RB_ - H_::RA + j].y);
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) dmma(ci[j][0], ci[j][1], s0, sb[j]);
+#pragma unroll
+    for (int j = 0; j < H_::CB_; ++j) dmma(ci[H_::CA + j][0], ci[H_::CA + j][1], s1, sb[H_::RB_ - H_::RA + j]);
+    a0 = a0n; a1 = a1n;
+    s0 = dadd_v(a0n.x, a0n.y); s1 = dadd_v(a1n.x, a1n.y);
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) { bv[j] = bn[j]; sb[j] = dadd_v(bn[j].x, bn[j].y); }
+  }
+#else
 #pragma unroll 2
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k = 4 * ks + q;
@@ -181,6 +310,17 @@ DEVINL void tri_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
 #pragma unroll
     for (int j = 0; j < H_::CB_; ++j) dmma(ci[H_::CA + j][0], ci[H_::CA + j][1], a1.y, bv[H_::RB_ - H_::RA + j].x);
   }
+#endif
+#if QOC_CMUL_3M
+#pragma unroll
+  for (int b = 0; b < H_::NB; ++b)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double t1 = cr[b][e], u = t2[b][e];
+      cr[b][e] = t1 - u;
+      ci[b][e] = ci[b][e] - t1 - u;
+    }
+#endif
 }
 
 // Store the warp's upper-triangle blocks of  U = X + Y  and mirror the strictly-upper blocks as
@@ -457,7 +597,9 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
     const int r = idx / n, c = idx - r * n;
     Xb[swz<NP>(r, c)] = p.U0[idx];
   }
-  for (int idx = tid; idx < m * n; idx += G) psi_b[idx] = p.V[idx];     // inter_vecs[0] = V (:233-234)
+  const bool want_psi = !p.chain_no_psi;
+  if (want_psi)
+    for (int idx = tid; idx < m * n; idx += G) psi_b[idx] = p.V[idx];   // inter_vecs[0] = V (:233-234)
 
   auto prefetch = [&](int t) {
     if (t < T) {
@@ -503,7 +645,7 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
     __syncthreads();                                  // P_t landed; X_t complete; step t-1 reads done
     const cplx* Xc = Xb + (NXB == 2 ? (t & 1) : 0) * T_::MAT;
     cplx* Xn = Xb + (NXB == 2 ? ((t + 1) & 1) : 0) * T_::MAT;
-    if (t > 0) extract(Xc, t);
+    if (t > 0 && want_psi) extract(Xc, t);
     prefetch(t + NPB - 1);
     if (PF32) {                                       // widen the raw fp32 tile into the swizzled operand buffer
       const float* src = Pstage + (t % NPB) * 2048;
@@ -521,7 +663,7 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
   cp_async_wait<0>();
   __syncthreads();
   const cplx* Xf = Xb + (NXB == 2 ? (T & 1) : 0) * T_::MAT;
-  extract(Xf, T);
+  if (want_psi) extract(Xf, T);
   cplx* Uf = p.Ufin + (size_t)b * nn;
   for (int idx = tid; idx < nn; idx += G) {
     const int r = idx / n, c = idx - r * n;
@@ -542,6 +684,82 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
     for (int w = 0; w < T_::WARPS; ++w) s += red[w];
     p.scal[(size_t)b * 8 + 5] = s / (double)n;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_segprod: (b, seg) -> Q_seg = P_{t1-1} ... P_{t0},  t0 = seg*L, t1 = min(T, t0+L).
+// U_final = X_T = P_{T-1} ... P_0 U0 and unitary_scale are NOT on the critical path of the loss or
+// the gradient when the states are propagated by k_vec_sweep, and only the total product is needed,
+// so the T-1 products are re-associated: B*ceil(T/L) independent segment products (this kernel,
+// tensor-pipe bound and perfectly balanced, unlike one sequential chain per instance) followed by a
+// ceil(T/L)-step chain over the segment matrices (k_chain_mma on the segment buffer).
+// One short-lived CTA per segment (so that higher-priority sweep CTAs get SM slots as segments
+// retire); X is updated in place, P_t double-buffered with cp.async.
+// ---------------------------------------------------------------------------------------------
+template <int NP, int RB, int CB>
+__global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p, int L, int S, cplx* __restrict__ seg_out) {
+  typedef MT<NP, RB, CB> T_;
+  constexpr int G = T_::THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* Xb = reinterpret_cast<cplx*>(smem_raw);            // [MAT]
+  cplx* Pb = Xb + T_::MAT;                                 // [2][MAT]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
+  const int n = p.n, T = p.T, nn = n * n;
+  const int ksteps = (n + 3) >> 2;
+  const int b = blockIdx.x / S, seg = blockIdx.x - b * S;
+  const int t0 = seg * L, len = min(L, T - t0);
+  const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + ((size_t)b * T + t0) * nn;
+
+  for (int i = tid; i < 3 * T_::MAT; i += G) Xb[i] = make_double2(0.0, 0.0);   // padding rows / columns stay zero
+  __syncthreads();
+  const int dr = G / n, dc = G - dr * n, r_first = tid / n, c_first = tid - r_first * n;
+  auto fetch = [&](int l, cplx* dst) {                     // P_{t0+l} -> swizzled operand buffer
+    if (l < len) {
+      const cplx* src = Pg + (size_t)l * nn + tid;
+      int r = r_first, c = c_first;
+      for (int idx = tid; idx < nn; idx += G, src += G) {
+        cp_async16(dst + swz<NP>(r, c), src);
+        r += dr; c += dc;
+        if (c >= n) { c -= n; ++r; }
+      }
+    }
+    cp_async_commit();
+  };
+  fetch(0, Xb);
+  fetch(1, Pb);
+  for (int l = 1; l < len; ++l) {
+    fetch(l + 1, Pb + (l & 1) * T_::MAT);                  // the buffer step l-1 used
+    cp_async_wait<1>();
+    __syncthreads();                                       // P_{t0+l} landed; X complete
+    double cr[RB][CB][2], ci[RB][CB][2];
+    mma_gemm<NP, RB, CB>(Pb + ((l - 1) & 1) * T_::MAT, Xb, cr, ci, rb0, cb0, ksteps, lane);
+    __syncthreads();                                       // in-place update: every warp has finished reading X
+    store_tile<NP, RB, CB>(Xb, cr, ci, rb0, cb0, lane);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  cplx* out = seg_out + (size_t)blockIdx.x * nn;
+  {
+    int r = r_first, c = c_first;
+    for (int idx = tid; idx < nn; idx += G) {
+      out[idx] = Xb[swz<NP>(r, c)];
+      r += dr; c += dc;
+      if (c >= n) { c -= n; ++r; }
+    }
+  }
+}
+
+template <int NP, int RB, int CB>
+cudaError_t launch_segprod(const QocParams& p, int L, int S, cplx* seg_out, cudaStream_t st) {
+  typedef MT<NP, RB, CB> T_;
+  const size_t smem = (size_t)3 * T_::MAT * sizeof(cplx);
+  cudaError_t e = cudaFuncSetAttribute(k_segprod<NP, RB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_segprod<NP, RB, CB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  k_segprod<NP, RB, CB><<<(unsigned)((size_t)p.B * S), T_::THREADS, smem, st>>>(p, L, S, seg_out);
+  return cudaGetLastError();
 }
 
 template <int NP, int RB, int CB>
@@ -571,6 +789,8 @@ cudaError_t launch_chain(const QocParams& p, cudaStream_t st) {
                            : (size_t)(NPB + NXB) * T_::MAT * sizeof(cplx);
   cudaError_t e = cudaFuncSetAttribute(k_chain_mma<NP, RB, CB, NPB, NXB, PF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_chain_mma<NP, RB, CB, NPB, NXB, PF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   k_chain_mma<NP, RB, CB, NPB, NXB, PF32><<<p.B, T_::THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
@@ -591,6 +811,13 @@ DEVINL void mma_gemm_ah(const cplx* __restrict__ A, const cplx* __restrict__ B, 
   for (int i = 0; i < RB; ++i)
 #pragma unroll
     for (int j = 0; j < CB; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+#if QOC_CMUL_3M
+  double t2[RB][CB][2];
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < CB; ++j) t2[i][j][0] = t2[i][j][1] = 0.0;
+#endif
   const int ac = 8 * rb0 + g, bc = 8 * cb0 + g;
 #pragma unroll 2
   for (int ks = 0; ks < ksteps; ++ks) {
@@ -603,6 +830,25 @@ DEVINL void mma_gemm_ah(const cplx* __restrict__ A, const cplx* __restrict__ B, 
     for (int i = 0; i < RB; ++i) { a[i] = Arow[(ac + 8 * i) ^ km]; a[i].y = -a[i].y; }
 #pragma unroll
     for (int j = 0; j < CB; ++j) b[j] = Brow[(bc + 8 * j) ^ km];
+#if QOC_CMUL_3M
+    double sa[RB], sb[CB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) sa[i] = a[i].x + a[i].y;
+#pragma unroll
+    for (int j = 0; j < CB; ++j) sb[j] = b[j].x + b[j].y;
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(t2[i][j][0], t2[i][j][1], a[i].y, b[j].y);
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], sa[i], sb[j]);
+#else
 #pragma unroll
     for (int i = 0; i < RB; ++i)
 #pragma unroll
@@ -621,7 +867,20 @@ DEVINL void mma_gemm_ah(const cplx* __restrict__ A, const cplx* __restrict__ B, 
     for (int i = 0; i < RB; ++i)
 #pragma unroll
       for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
+#endif
   }
+#if QOC_CMUL_3M
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < CB; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double t1 = cr[i][j][e], u = t2[i][j][e];
+        cr[i][j][e] = t1 - u;
+        ci[i][j][e] = ci[i][j][e] - t1 - u;
+      }
+#endif
 }
 
 template <int NP, int RB, int CB, int NPB, int NLB>
@@ -838,6 +1097,21 @@ cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaSt
   return cudaErrorInvalidValue;
 }
 
+cudaError_t qoc_launch_segprod_f64(const QocParams& p, int NP, int L, int S, cplx* seg_out, cudaStream_t st, int64_t* launches) {
+  ++*launches;
+  switch (NP) {
+    case 8: return launch_segprod<8, 1, 1>(p, L, S, seg_out, st);
+    case 16: return launch_segprod<16, 2, 2>(p, L, S, seg_out, st);
+    case 24: return launch_segprod<24, 1, 3>(p, L, S, seg_out, st);
+    case 32: return launch_segprod<32, 2, 4>(p, L, S, seg_out, st);
+    case 40: return launch_segprod<40, 1, 5>(p, L, S, seg_out, st);
+    case 48: return launch_segprod<48, 2, 3>(p, L, S, seg_out, st);
+    case 56: return launch_segprod<56, 1, 7>(p, L, S, seg_out, st);
+    case 64: return launch_segprod<64, 2, 4>(p, L, S, seg_out, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaStream_t st, int64_t* launches) {
   ++*launches;
   if (p_is_f32) {                                     // tcgen05 path: n <= 32
@@ -848,6 +1122,13 @@ cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaS
       case 32: return launch_chain<32, 1, 2, 3, 2, true>(p, st);
     }
     return cudaErrorInvalidValue;
+  }
+  if (p.chain_no_psi) {                               // runs beside k_vec_sweep: two propagator buffers leave room for it
+    switch (NP) {
+      case 32: return launch_chain<32, 1, 2, 2, 2>(p, st);
+      case 40: return launch_chain<40, 1, 5, 2, 2>(p, st);
+      case 48: return launch_chain<48, 1, 3, 2, 2>(p, st);
+    }
   }
   switch (NP) {
     case 8: return launch_chain<8, 1, 1, 3, 2>(p, st);

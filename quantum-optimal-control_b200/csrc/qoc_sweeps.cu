@@ -391,6 +391,7 @@ cudaError_t qoc_launch_dress(const QocParams& p, int phase, cudaStream_t st, int
 
 cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* launches) {
   ++*launches;
+  cudaFuncSetAttribute(k_fwd_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   k_fwd_reduce<<<p.B, 256, 0, st>>>(p);
   return cudaGetLastError();
 }
