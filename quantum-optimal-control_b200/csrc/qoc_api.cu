@@ -339,7 +339,7 @@ static QocParams chunk_params(const QocParams& p, const qoc_dims_t& d, int b0, i
 // is re-associated into segment products (k_segprod) + a short chain and runs on the caller's stream
 // beside it.  QOC_B200_NO_VEC_SWEEP=1 restores the single-stream chain.
 static bool use_vec_sweeps(qoc_handle_t h, const QocParams& p) {
-  static const bool off = getenv("QOC_B200_NO_VEC_SWEEP") != nullptr;
+  const bool off = getenv("QOC_B200_NO_VEC_SWEEP") != nullptr;     // read per call: tests flip it
   return !off && h->d.dtype == QOC_F64 && h->d.n <= 64 && 2 * h->d.m < h->NP && qoc_vec_sweep_supported(p);
 }
 

@@ -6,18 +6,19 @@
 //                       (the reverse sweep TF autodiff performs through :214-220)
 //
 // Both are T dependent n x n x m matrix-vector products per instance: 16 n^2 bytes of P_t against
-// 8 n^2 m flops per step, i.e. HBM-bound once the per-step latency is out of the way -- and a lone
-// warp issues at ~0.3 IPC, so the step is spread over many warps.  One CTA per instance, WK x CP
-// warps: warp (wk, cp) owns the summation slice k = wk (mod WK) and the column pairs cp, cp+CP, ...;
-// lane l owns rows l and l+32 of the result.  A step is
-//   barrier | partial[wk][j][l] = sum_{k in slice} ring[k][l] * v_j[k] | barrier | sum the WK
-//   partials, add the regulariser source, write v_j(next) to shared memory and psi / lambda to HBM
-// P_t is streamed by cp.async into an NST-deep ring, laid out so that the 32 lanes of a warp read 32
-// consecutive 16-byte elements (conflict-free):
-//   forward : ring[k][l] = P_t[l][k]   (transposing scatter; 16-byte granularity makes it free)
-//   reverse : ring[k][l] = P_t[k][l]   (straight copy), used conjugated
-// The four real partial sums per complex product live in separate accumulators (independent DFMA
-// chains, 8.4-cycle latency at 2.3 cycles per warp instruction: tools/dmma_probe.cu).
+// 8 n^2 m flops per step, i.e. HBM-bound once the per-step latency is out of the way -- and that
+// latency is instruction issue (a lone warp runs at ~0.3 IPC), so a step is spread over WK x CP
+// warps and stripped to the bone:
+//   * P_t arrives by ONE bulk-copy instruction (TMA, cp.async.bulk 1-D, 16 n^2 contiguous bytes)
+//     into an NST-deep ring, completion on an mbarrier per stage -- no per-thread copy loop;
+//   * warp (wk, cp) owns the summation slice k = wk (mod WK) and the column pairs cp, cp+CP, ...;
+//     lane l owns rows l (and l+32); every shared-memory offset of the k loop is loop-invariant;
+//   * barrier | partial[wk][j][l] = sum_{k in slice} P(k,l) v_j[k] | barrier | threads (j,l): sum the
+//     WK partials, add the regulariser source, write v_j(next) to shared memory and psi/lambda to HBM.
+// The ring keeps the row-major layout of HBM: the reverse sweep (P^dagger) reads rows (lanes
+// contiguous, conflict-free); the forward sweep reads columns (lane stride n: 2-way bank conflicts
+// for n = 30, irrelevant at 8 loads per step).  The four real partial sums per complex product live
+// in separate accumulators (independent DFMA chains, 8.4-cycle latency: tools/dmma_probe.cu).
 #include "qoc_internal.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -26,13 +27,28 @@
 
 namespace {
 
-DEVINL void cp_async16(void* smem_dst, const void* gmem_src) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVINL void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// 1-D bulk copy global -> shared (TMA), completion counted in bytes on `bar`
+DEVINL void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 DEVINL cplx cmul(const cplx a, const cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
@@ -50,61 +66,56 @@ SweepShape sweep_shape(int n, int m) {
   s.npairs = (m + 1) / 2;
   s.cp = s.npairs < 4 ? s.npairs : 4;
   const int mp = 2 * s.npairs;                   // columns rounded up to pairs
-  // ring + vectors [2][mp][VL] + partials [WK][mp][VL]
-  s.smem = ((size_t)NST * n * (n | 1) + 32 + (size_t)(2 + WK) * mp * NR * 32) * sizeof(cplx);
+  // ring (+ slack for the padded lanes of the last row) + vectors [2][mp][VL] + partials [WK][mp][VL] + mbarriers
+  s.smem = ((size_t)NST * n * n + 64 + (size_t)(2 + WK) * mp * NR * 32) * sizeof(cplx) + 8 * NST;
   return s;
 }
 
 template <bool REV, int NR, int NST>
 __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int VL = NR * 32;
+  constexpr int KI = VL / WK;                    // k iterations per warp (upper bound, predicated on k < n)
   const int n = p.n, m = p.m, T = p.T, nn = n * n, mn = m * n;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int wk = warp % WK, cp0 = warp / WK;
   const int npairs = (m + 1) >> 1, mp = 2 * npairs;
   const int b = blockIdx.x;
-  // ring stage: n rows of LD elements; LD odd so that the transposing scatter of the forward sweep (lanes
-  // along k, stride LD) and the row reads (lanes along l) are both bank-conflict free
-  const int LD = n | 1, stage = n * LD;
-  cplx* ring = reinterpret_cast<cplx*>(smem_raw);                       // [NST][n][LD] (+32 slack for the padded lanes)
-  cplx* vecs = ring + (size_t)NST * stage + 32;                         // [2][mp][VL]
+  cplx* ring = reinterpret_cast<cplx*>(smem_raw);                       // [NST][n][n] row-major, as in HBM
+  cplx* vecs = ring + (size_t)NST * nn + 64;                            // [2][mp][VL]
   cplx* part = vecs + (size_t)2 * mp * VL;                              // [WK][mp][VL]
+  uint64_t* full = reinterpret_cast<uint64_t*>(part + (size_t)WK * mp * VL);   // [NST]
   const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * nn;
   cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
   cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn;
   const int nsteps = REV ? T - 1 : T;
+  const uint32_t stage_bytes = (uint32_t)nn * sizeof(cplx);
 
-  // P_step -> ring stage (step index in sweep order); fwd: transposing scatter
-  const int dr = nt / n, dc = nt - dr * n, r_first = tid / n, c_first = tid - r_first * n;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // P_step -> ring stage (step index in sweep order); issued by one thread
   auto prefetch = [&](int step) {
     if (step < nsteps) {
       const int t = REV ? T - 1 - step : step;
-      const cplx* src = Pg + (size_t)t * nn + tid;
-      cplx* dst = ring + (size_t)(step % NST) * stage;
-      int r = r_first, c = c_first;
-      if (REV) {
-        for (int idx = tid; idx < nn; idx += nt, src += nt) {
-          cp_async16(dst + r * LD + c, src);
-          r += dr; c += dc;
-          if (c >= n) { c -= n; ++r; }
-        }
-      } else {
-        for (int idx = tid; idx < nn; idx += nt, src += nt) {
-          cp_async16(dst + c * LD + r, src);
-          r += dr; c += dc;
-          if (c >= n) { c -= n; ++r; }
-        }
-      }
+      uint64_t* bar = &full[step % NST];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage (ordered by the barrier) before the async write
+      mbar_expect_tx(bar, stage_bytes);
+      bulk_g2s(ring + (size_t)(step % NST) * nn, Pg + (size_t)t * nn, stage_bytes, bar);
     }
-    cp_async_commit();
   };
+  if (tid == 0) {
 #pragma unroll
-  for (int i = 0; i < NST - 1; ++i) prefetch(i);
+    for (int i = 0; i < NST - 1; ++i) prefetch(i);
+  }
 
   // regulariser sources of the costate recursion (core/regularization_functions.py:71-95)
   const bool forb = REV && p.reg.has_forbidden && p.fw != nullptr;
   const bool spd = REV && p.reg.has_speed_up != 0;
+  const bool has_src = forb || spd;
   const double* sc = p.scal + (size_t)b * 8;
   const double spdfac = REV ? sc[4] : 0.0;
   auto source = [&](int t, int j, int r) -> cplx {
@@ -143,41 +154,57 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
       }
     }
     vecs[e] = v;
+    vecs[(size_t)mp * VL + e] = make_double2(0.0, 0.0);
   }
+
+  // loop-invariant element offsets of the k loop: reverse P[k][l] -> k*n + l, forward P[l][k] -> l*n + k;
+  // rows / columns beyond n are clamped (their products are discarded or multiplied by v = 0)
+  int moff[KI][NR];
+#pragma unroll
+  for (int i = 0; i < KI; ++i)
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) {
+      const int k = min(wk + WK * i, n - 1), l = min(lane + 32 * rr, n - 1);
+      moff[i][rr] = REV ? k * n + l : l * n + k;
+    }
+  // the element this thread finalises
+  const int fj = tid / VL, fr = tid - fj * VL;
+  const bool fin = tid < mp * VL, fval = fin && fj < m && fr < n;
+  const size_t fout = (size_t)fj * n + fr;
 
   int cur = 0;
   for (int step = 0; step < nsteps; ++step) {
-    cp_async_wait<NST - 2>();
-    __syncthreads();                             // stage `step` landed; v(cur) complete; stage step-1 and partials free
-    prefetch(step + NST - 1);
+    __syncthreads();                             // v(cur) complete; stage step-1 and the partials are free
+    if (tid == 0) prefetch(step + NST - 1);
     const int t = REV ? T - 1 - step : step;     // propagator index; result is lambda(t) / psi(t+1)
-    // the source of the element this thread finalises (first pass of the loop below), issued early
     cplx src0 = make_double2(0.0, 0.0);
+    if (has_src && fval) src0 = source(t, fj, fr);       // issued early, consumed after the second barrier
     {
-      const int j = tid / VL, r = tid - j * VL;
-      if (REV && tid < mp * VL && j < m && r < n) src0 = source(t, j, r);
+      uint64_t* bar = &full[step % NST];
+      const uint32_t parity = (uint32_t)(step / NST) & 1u;
+      while (!mbar_try_wait(bar, parity)) {}
     }
-    const cplx* M = ring + (size_t)(step % NST) * stage + lane;
+    const cplx* M = ring + (size_t)(step % NST) * nn;
     for (int pr = cp0; pr < npairs; pr += CP) {
-      const cplx* va = vecs + ((size_t)cur * mp + 2 * pr) * VL;
+      const cplx* va = vecs + ((size_t)cur * mp + 2 * pr) * VL + wk;
       const cplx* vb = va + VL;
       double a0[NR][4], a1[NR][4];               // partial sums  xx, yy, xy, yx
 #pragma unroll
       for (int rr = 0; rr < NR; ++rr)
 #pragma unroll
         for (int e = 0; e < 4; ++e) a0[rr][e] = a1[rr][e] = 0.0;
-      const cplx* Mk = M + (size_t)wk * LD;
-#pragma unroll 4
-      for (int k = wk; k < n; k += WK, Mk += WK * LD) {
-        const cplx x = va[k], y = vb[k];
 #pragma unroll
-        for (int rr = 0; rr < NR; ++rr) {
-          cplx e = make_double2(0.0, 0.0);
-          if (NR == 1 || lane + 32 * rr < n) e = Mk[32 * rr];
-          a0[rr][0] = fma(e.x, x.x, a0[rr][0]); a0[rr][1] = fma(e.y, x.y, a0[rr][1]);
-          a0[rr][2] = fma(e.x, x.y, a0[rr][2]); a0[rr][3] = fma(e.y, x.x, a0[rr][3]);
-          a1[rr][0] = fma(e.x, y.x, a1[rr][0]); a1[rr][1] = fma(e.y, y.y, a1[rr][1]);
-          a1[rr][2] = fma(e.x, y.y, a1[rr][2]); a1[rr][3] = fma(e.y, y.x, a1[rr][3]);
+      for (int i = 0; i < KI; ++i) {
+        if (wk + WK * i < n) {                   // warp-uniform
+          const cplx x = va[WK * i], y = vb[WK * i];
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) {
+            const cplx e = M[moff[i][rr]];
+            a0[rr][0] = fma(e.x, x.x, a0[rr][0]); a0[rr][1] = fma(e.y, x.y, a0[rr][1]);
+            a0[rr][2] = fma(e.x, x.y, a0[rr][2]); a0[rr][3] = fma(e.y, x.x, a0[rr][3]);
+            a1[rr][0] = fma(e.x, y.x, a1[rr][0]); a1[rr][1] = fma(e.y, y.y, a1[rr][1]);
+            a1[rr][2] = fma(e.x, y.y, a1[rr][2]); a1[rr][3] = fma(e.y, y.x, a1[rr][3]);
+          }
         }
       }
       cplx* pa = part + ((size_t)wk * mp + 2 * pr) * VL + lane;
@@ -195,20 +222,25 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
     __syncthreads();
     const int nxt = cur ^ 1;
     cplx* out = REV ? lam_b + (size_t)t * mn : psi_b + (size_t)(t + 1) * mn;
-    for (int e = tid; e < mp * VL; e += nt) {
+    if (fval) {
+      cplx v = src0;
+#pragma unroll
+      for (int w = 0; w < WK; ++w) { const cplx q = part[(size_t)w * mp * VL + tid]; v.x += q.x; v.y += q.y; }
+      out[fout] = v;
+      vecs[(size_t)nxt * mp * VL + tid] = v;
+    }
+    for (int e = tid + nt; e < mp * VL; e += nt) {           // more than nt elements (many columns, n > 32)
       const int j = e / VL, r = e - j * VL;
-      cplx v = make_double2(0.0, 0.0);
       if (j < m && r < n) {
-        v = (REV && e != tid) ? source(t, j, r) : src0;
+        cplx v = has_src ? source(t, j, r) : make_double2(0.0, 0.0);
 #pragma unroll
         for (int w = 0; w < WK; ++w) { const cplx q = part[(size_t)w * mp * VL + e]; v.x += q.x; v.y += q.y; }
         out[(size_t)j * n + r] = v;
+        vecs[(size_t)nxt * mp * VL + e] = v;
       }
-      vecs[(size_t)nxt * mp * VL + e] = v;
     }
     cur = nxt;
   }
-  cp_async_wait<0>();
 }
 
 template <bool REV, int NR, int NST>
@@ -232,18 +264,17 @@ bool qoc_vec_sweep_supported(const QocParams& p) {
   return smem <= 200 * 1024;
 }
 
-// ring depth: the sweeps are limited by the bytes they keep in flight (HBM latency under load is ~2 us),
-// so 5 stages when two CTAs of that size still leave an SM room for the U_final branch, else 3
+// ring depth: 4 stages when two CTAs of that size still leave an SM room for the U_final branch, else 3
 cudaError_t qoc_launch_vec_sweep(const QocParams& p, int reverse, cudaStream_t st, int64_t* launches) {
   if (!qoc_vec_sweep_supported(p)) return cudaErrorNotSupported;
   ++*launches;
   static const int force = getenv("QOC_B200_SWEEP_STAGES") ? atoi(getenv("QOC_B200_SWEEP_STAGES")) : 0;
   if (p.n > 32) {
-    const bool deep = force ? force >= 5 : sweep_shape<2, 5>(p.n, p.m).smem <= 84 * 1024;
-    if (deep) return reverse ? launch<true, 2, 5>(p, st) : launch<false, 2, 5>(p, st);
+    const bool deep = force ? force >= 4 : sweep_shape<2, 4>(p.n, p.m).smem <= 84 * 1024;
+    if (deep) return reverse ? launch<true, 2, 4>(p, st) : launch<false, 2, 4>(p, st);
     return reverse ? launch<true, 2, 3>(p, st) : launch<false, 2, 3>(p, st);
   }
-  const bool deep = force ? force >= 5 : sweep_shape<1, 5>(p.n, p.m).smem <= 84 * 1024;
-  if (deep) return reverse ? launch<true, 1, 5>(p, st) : launch<false, 1, 5>(p, st);
+  const bool deep = force ? force >= 4 : sweep_shape<1, 4>(p.n, p.m).smem <= 84 * 1024;
+  if (deep) return reverse ? launch<true, 1, 4>(p, st) : launch<false, 1, 4>(p, st);
   return reverse ? launch<true, 1, 3>(p, st) : launch<false, 1, 3>(p, st);
 }

@@ -345,6 +345,80 @@ def test_full_size_c3_properties(built_lib):
     eng.close()
 
 
+# ---- few-state path: vector sweeps (TMA ring) + re-associated U_final (segment products) ---------------
+SWEEP_CASES = {
+    # T > 48 -> the U_final branch runs as 16-step segment products + a chain over the segments
+    'c2_T100_regs': (lambda: W.c2_transmon_cavity(T=100), dict(total_time=200.0, reg_coeffs=ALL_REGS), 3),
+    'c2_T67': (lambda: W.c2_transmon_cavity(T=67), dict(total_time=134.0), 2),           # last segment has 3 steps
+    'c2_T65': (lambda: W.c2_transmon_cavity(T=65), dict(total_time=130.0), 1),           # last segment has 1 step
+    # n = 36 (two rows per lane), m = 4, forbidden-state sources in the costate sweep
+    'c3_T70_forbidden': (lambda: W.c3_two_transmon_cnot(T=70), dict(total_time=0.7), 2),
+    # odd m (a padded column), U0 != identity, n not a multiple of 4
+    'n13_m3_U0': (lambda: W.c5_random(13, T=60), dict(U0=np.linalg.qr(np.random.default_rng(8).normal(size=(13, 13)) +
+                                                                       1j * np.random.default_rng(9).normal(size=(13, 13)))[0],
+                                                       states_concerned_list=[0, 4, 12],
+                                                       reg_coeffs={'speed_up': 0.3, 'forbidden_coeff_list': [2.0], 'states_forbidden_list': [7]}), 2),
+    # many columns on one CTA (m = 11 < NP/2 = 12): column pairs are looped over inside a warp
+    'n24_m11': (lambda: W.c5_random(24, T=52), dict(states_concerned_list=list(range(11))), 1),
+}
+
+
+@pytest.mark.parametrize("name", list(SWEEP_CASES))
+def test_vec_sweep_path_matches_oracle_and_single_stream_path(name, built_lib, monkeypatch):
+    """The few-state path (k_vec_sweep on the high-priority stream, k_segprod + chain for U_final) against the
+    oracle AND against the single-stream chain/costate kernels it replaces (QOC_B200_NO_VEC_SWEEP=1)."""
+    fn, over, B = SWEEP_CASES[name]
+    setups, guess, args, kw = make_case(fn(), seed=23, B=B, **over)
+    sp, eng = engine_for(args, kw, guess)
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    n_launch0 = eng.launch_count
+    out = {k: v.clone() for k, v in eng.value_and_grad(base).items()}
+    n_launch = eng.launch_count - n_launch0
+    ev = {k: (None if v is None else v.clone()) for k, v in eng.evolve(base).items()}
+    torch.cuda.synchronize()
+    monkeypatch.setenv("QOC_B200_NO_VEC_SWEEP", "1")
+    n_launch0 = eng.launch_count
+    old = {k: v.clone() for k, v in eng.value_and_grad(base).items()}
+    assert eng.launch_count - n_launch0 < n_launch            # the switch really selected the other kernels
+    ev_old = eng.evolve(base)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("QOC_B200_NO_VEC_SWEEP")
+    for k in ('loss', 'reg_loss', 'unitary_scale', 'grad_squared'):
+        assert (out[k] - old[k]).abs().max().item() < 1e-11 * max(1.0, old[k].abs().max().item()), k
+    assert (out['grad'] - old['grad']).abs().max().item() < 1e-11 * old['grad'].abs().max().item()
+    assert (ev['U_final'] - ev_old['U_final']).abs().max().item() < 1e-11
+    assert (ev['inter_vecs'] - ev_old['inter_vecs']).abs().max().item() < 1e-11
+    for b in range(B):
+        ref = O.graph_value_and_grad(setups[b], setups[b].ops_weight_base)
+        n = setups[b].n
+        assert np.linalg.norm(ev['U_final'][b].cpu().numpy() - O.r_to_c_mat(ref.final_state, n)) < ATOL_U
+        iv_ref = np.transpose(ref.inter_vecs[:, :n, :] + 1j * ref.inter_vecs[:, n:, :], (2, 0, 1))
+        assert np.abs(ev['inter_vecs'][b].cpu().numpy() - iv_ref).max() < ATOL_U
+        assert abs(out['loss'][b].item() - ref.loss) < 1e-10
+        assert abs(out['reg_loss'][b].item() - ref.reg_loss) < 1e-10 * max(1.0, abs(ref.reg_loss))
+        assert abs(out['unitary_scale'][b].item() - ref.unitary_scale) < 1e-10
+        assert np.abs(out['grad'][b].cpu().numpy() - ref.grad).max() < RTOL_G * max(np.abs(ref.grad).max(), 1e-300)
+    eng.close()
+
+
+def test_value_and_grad_is_repeatable_across_streams(built_lib):
+    """Back-to-back calls reuse the propagator workspace while the high-priority branch of the previous call
+    may still be reading it: results must not depend on that (joins are in place)."""
+    setups, guess, args, kw = make_case(W.c2_transmon_cavity(T=80), seed=41, B=16, total_time=160.0)
+    sp, eng = engine_for(args, kw, guess)
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    first = {k: v.clone() for k, v in eng.value_and_grad(base).items()}
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(5):
+            out = eng.value_and_grad(base)
+        again = {k: v.clone() for k, v in out.items()}
+    s.synchronize()
+    for k in first:
+        assert torch.equal(first[k], again[k]), k
+    eng.close()
+
+
 def test_batch_chunking_gives_identical_results(built_lib, monkeypatch):
     """A workspace budget smaller than the full batch makes the library process the batch in chunks
     (qoc_batch_chunk < B); every output must be bit-identical to the single-pass run."""
