@@ -27,7 +27,10 @@
  *     problem constants and differ only in their control amplitudes;
  *   - "dev" pointers are device pointers owned by the caller (e.g. torch tensors), "host"
  *     pointers are host memory; `stream` is a cudaStream_t passed as void*; device entry points
- *     are asynchronous on that stream, *_host entry points synchronise it before returning;
+ *     are asynchronous on that stream, *_host entry points synchronise it before returning; a handle
+ *     also owns one high-priority stream on which the loss / gradient kernels of few-state problems
+ *     run beside the U_final kernels -- it forks from and joins back into `stream` inside every call,
+ *     so the caller only ever orders against `stream`;
  *   - return value 0 = ok, negative = QOC_E* below; qoc_last_error(h) gives the message;
  *   - a handle is not thread-safe; distinct handles are independent;
  *   - there is NO CPU fallback: every compute entry point fails with QOC_ECUDA when no sm_100
@@ -165,9 +168,11 @@ int64_t qoc_launch_count(qoc_handle_t h);
  * (the tcgen05 pipeline bails out instead of hanging if an MMA completion barrier never fires). */
 int qoc_poll_error(qoc_handle_t h, void* stream);
 
-/* Optional per-kernel timing with CUDA events recorded on the call's stream around each of the
- * QOC_NUM_KERNELS launches of the last qoc_value_and_grad (order: expm, chain, fwd_reduce, costate,
- * grad, finalize).  qoc_kernel_times_ms synchronises on the last event. */
+/* Optional per-stage timing with CUDA events recorded around the QOC_NUM_KERNELS stages of the last
+ * qoc_value_and_grad on the stream each stage runs on (order: expm, chain, fwd_reduce, costate, grad,
+ * finalize).  For few-state problems "chain" is the forward state sweep (the U_final kernels run
+ * concurrently on the caller's stream) and "finalize" includes the join of the two branches.
+ * qoc_kernel_times_ms synchronises on the last event. */
 #define QOC_NUM_KERNELS 6
 int qoc_set_profiling(qoc_handle_t h, int enable);
 int qoc_kernel_times_ms(qoc_handle_t h, float* ms_out /* [QOC_NUM_KERNELS] */);
