@@ -358,7 +358,9 @@ static int join_hi(qoc_handle_t h, cudaStream_t st) {
 static int launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   QocParams q = p;
   q.chain_no_psi = 1;
-  const int L = QOC_SEG_LEN, S = (p.T + L - 1) / L;
+  int L = QOC_SEG_LEN;
+  if (getenv("QOC_B200_SEG_LEN")) { L = atoi(getenv("QOC_B200_SEG_LEN")); if (L < QOC_SEG_LEN) L = QOC_SEG_LEN; }   // experiments: longer segments only
+  const int S = (p.T + L - 1) / L;
   if (S >= 4) {
     CUDA_TRY(h, qoc_launch_segprod_f64(p, h->NP, L, S, h->seg, st, &h->launches));
     q.P = h->seg; q.T = S;

@@ -707,7 +707,9 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
   const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
   const int n = p.n, T = p.T, nn = n * n;
   const int ksteps = (n + 3) >> 2;
-  const int b = blockIdx.x / S, seg = blockIdx.x - b * S;
+  // segment-major dispatch: the CTAs of one time segment of ALL instances run together, at the pace at which the
+  // forward sweep (all instances in lock step) moves through the same propagators -> the second reader hits L2
+  const int seg = blockIdx.x / p.B, b = blockIdx.x - seg * p.B;
   const int t0 = seg * L, len = min(L, T - t0);
   const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + ((size_t)b * T + t0) * nn;
 
@@ -739,7 +741,7 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
   }
   cp_async_wait<0>();
   __syncthreads();
-  cplx* out = seg_out + (size_t)blockIdx.x * nn;
+  cplx* out = seg_out + ((size_t)b * S + seg) * nn;
   {
     int r = r_first, c = c_first;
     for (int idx = tid; idx < nn; idx += G) {

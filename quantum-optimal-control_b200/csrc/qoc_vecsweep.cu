@@ -60,18 +60,18 @@ struct SweepShape {
   size_t smem;
 };
 
-template <int NR, int NST>
+template <int NR, int NST, int CPW = 2>
 SweepShape sweep_shape(int n, int m) {
   SweepShape s;
-  s.npairs = (m + 1) / 2;
+  s.npairs = (m + CPW - 1) / CPW;                // column groups (CPW columns per warp)
   s.cp = s.npairs < 4 ? s.npairs : 4;
-  const int mp = 2 * s.npairs;                   // columns rounded up to pairs
+  const int mp = CPW * s.npairs;                 // columns rounded up to whole groups
   // ring (+ slack for the padded lanes of the last row) + vectors [2][mp][VL] + partials [WK][mp][VL] + mbarriers
   s.smem = ((size_t)NST * n * n + 64 + (size_t)(2 + WK) * mp * NR * 32) * sizeof(cplx) + 8 * NST;
   return s;
 }
 
-template <bool REV, int NR, int NST>
+template <bool REV, int NR, int NST, int CPW>
 __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int VL = NR * 32;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
   const int n = p.n, m = p.m, T = p.T, nn = n * n, mn = m * n;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int wk = warp % WK, cp0 = warp / WK;
-  const int npairs = (m + 1) >> 1, mp = 2 * npairs;
+  const int npairs = (m + CPW - 1) / CPW, mp = CPW * npairs;
   const int b = blockIdx.x;
   cplx* ring = reinterpret_cast<cplx*>(smem_raw);                       // [NST][n][n] row-major, as in HBM
   cplx* vecs = ring + (size_t)NST * nn + 64;                            // [2][mp][VL]
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
     }
     const cplx* M = ring + (size_t)(step % NST) * nn;
     for (int pr = cp0; pr < npairs; pr += CP) {
-      const cplx* va = vecs + ((size_t)cur * mp + 2 * pr) * VL + wk;
-      const cplx* vb = va + VL;
+      const cplx* va = vecs + ((size_t)cur * mp + CPW * pr) * VL + wk;
+      const cplx* vb = va + (CPW - 1) * VL;
       double a0[NR][4], a1[NR][4];               // partial sums  xx, yy, xy, yx
 #pragma unroll
       for (int rr = 0; rr < NR; ++rr)
@@ -196,26 +196,28 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
 #pragma unroll
       for (int i = 0; i < KI; ++i) {
         if (wk + WK * i < n) {                   // warp-uniform
-          const cplx x = va[WK * i], y = vb[WK * i];
+          const cplx x = va[WK * i], y = CPW == 2 ? vb[WK * i] : x;
 #pragma unroll
           for (int rr = 0; rr < NR; ++rr) {
             const cplx e = M[moff[i][rr]];
             a0[rr][0] = fma(e.x, x.x, a0[rr][0]); a0[rr][1] = fma(e.y, x.y, a0[rr][1]);
             a0[rr][2] = fma(e.x, x.y, a0[rr][2]); a0[rr][3] = fma(e.y, x.x, a0[rr][3]);
-            a1[rr][0] = fma(e.x, y.x, a1[rr][0]); a1[rr][1] = fma(e.y, y.y, a1[rr][1]);
-            a1[rr][2] = fma(e.x, y.y, a1[rr][2]); a1[rr][3] = fma(e.y, y.x, a1[rr][3]);
+            if (CPW == 2) {
+              a1[rr][0] = fma(e.x, y.x, a1[rr][0]); a1[rr][1] = fma(e.y, y.y, a1[rr][1]);
+              a1[rr][2] = fma(e.x, y.y, a1[rr][2]); a1[rr][3] = fma(e.y, y.x, a1[rr][3]);
+            }
           }
         }
       }
-      cplx* pa = part + ((size_t)wk * mp + 2 * pr) * VL + lane;
+      cplx* pa = part + ((size_t)wk * mp + CPW * pr) * VL + lane;
 #pragma unroll
       for (int rr = 0; rr < NR; ++rr) {
         if (REV) {                               // conj(e) * v
           pa[32 * rr] = make_double2(a0[rr][0] + a0[rr][1], a0[rr][2] - a0[rr][3]);
-          pa[VL + 32 * rr] = make_double2(a1[rr][0] + a1[rr][1], a1[rr][2] - a1[rr][3]);
+          if (CPW == 2) pa[VL + 32 * rr] = make_double2(a1[rr][0] + a1[rr][1], a1[rr][2] - a1[rr][3]);
         } else {
           pa[32 * rr] = make_double2(a0[rr][0] - a0[rr][1], a0[rr][2] + a0[rr][3]);
-          pa[VL + 32 * rr] = make_double2(a1[rr][0] - a1[rr][1], a1[rr][2] + a1[rr][3]);
+          if (CPW == 2) pa[VL + 32 * rr] = make_double2(a1[rr][0] - a1[rr][1], a1[rr][2] + a1[rr][3]);
         }
       }
     }
@@ -243,17 +245,26 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
   }
 }
 
-template <bool REV, int NR, int NST>
-cudaError_t launch(const QocParams& p, cudaStream_t st) {
-  const SweepShape s = sweep_shape<NR, NST>(p.n, p.m);
-  cudaError_t e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+template <bool REV, int NR, int NST, int CPW>
+cudaError_t launch_cpw(const QocParams& p, cudaStream_t st) {
+  const SweepShape s = sweep_shape<NR, NST, CPW>(p.n, p.m);
+  cudaError_t e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
   if (e != cudaSuccess) return e;
   // same (maximal) shared-memory carve-out as the kernels it runs beside: CTAs of kernels that ask
   // for different carve-outs cannot share an SM
-  e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST, CPW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  k_vec_sweep<REV, NR, NST><<<p.B, 32 * WK * s.cp, s.smem, st>>>(p, s.cp);
+  k_vec_sweep<REV, NR, NST, CPW><<<p.B, 32 * WK * s.cp, s.smem, st>>>(p, s.cp);
   return cudaGetLastError();
+}
+
+// two columns per warp; QOC_B200_SWEEP_CPW=1 gives every column its own warp (half the dependent DFMAs per warp
+// and step: the sweeps alone get ~5 % faster, the step does not -- the U_final branch becomes the longer one)
+template <bool REV, int NR, int NST>
+cudaError_t launch(const QocParams& p, cudaStream_t st) {
+  static const int force = getenv("QOC_B200_SWEEP_CPW") ? atoi(getenv("QOC_B200_SWEEP_CPW")) : 0;
+  const bool one = force == 1;
+  return one ? launch_cpw<REV, NR, NST, 1>(p, st) : launch_cpw<REV, NR, NST, 2>(p, st);
 }
 
 }  // namespace
