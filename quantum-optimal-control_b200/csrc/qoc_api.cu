@@ -234,7 +234,16 @@ int qoc_set_problem(qoc_handle_t h, const double* A_host, const double* U0_host,
     }
   h->pat_n = (int)prc.size();
   CUDA_TRY(h, upload(&h->pat_rc, prc.data(), prc.size(), st));
-  CUDA_TRY(h, upload(&h->pat_coef, pcf.data(), pcf.size() / 2, st));
+  {   // fp64 table k-major ([K+1][pat_n]) so that the H assembly of k_expm_mma reads it coalesced
+    const size_t pn = prc.size();
+    std::vector<double> pkm(pcf.size());
+    for (size_t e = 0; e < pn; ++e)
+      for (int k = 0; k <= d.K; ++k) {
+        pkm[((size_t)k * pn + e) * 2] = pcf[(e * (d.K + 1) + k) * 2];
+        pkm[((size_t)k * pn + e) * 2 + 1] = pcf[(e * (d.K + 1) + k) * 2 + 1];
+      }
+    CUDA_TRY(h, upload(&h->pat_coef, pkm.data(), pkm.size() / 2, st));
+  }
   std::vector<float> pcf32(pcf.begin(), pcf.end());
   CUDA_TRY(h, upload(&h->pat_coef_f, pcf32.data(), pcf32.size() / 2, st));
   CUDA_TRY(h, upload(&h->A, A_host, (size_t)(d.K + 1) * nn, st));

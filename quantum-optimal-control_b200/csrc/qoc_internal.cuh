@@ -35,7 +35,7 @@ struct QocParams {
   const cplx* coo_v;    // [nnz]
   int pat_n;            // union sparsity pattern of A_0..A_K
   const int* pat_rc;    // [pat_n]  (row << 16) | col
-  const cplx* pat_coef; // [pat_n][K+1]
+  const cplx* pat_coef; // [K+1][pat_n] (k-major)
   const float2* pat_coef_f;  // same in fp32 (tcgen05 path)
   qoc_reg_t reg;
   // per-call

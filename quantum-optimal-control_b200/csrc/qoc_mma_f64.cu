@@ -406,8 +406,13 @@ DEVINL void herm_taylor(const QocParams& p, const cplx* Hs, cplx* buf1, cplx* bu
 // ---------------------------------------------------------------------------------------------
 // k_expm_mma: persistent over (b,t) items.  An item is owned by WARPS warps; when WARPS == 1 a
 // CTA carries 4 independent items (one per warp), else exactly one.  Shared memory per item:
-// H, ping, pong (3 x NP^2 x 16 B) + 32 weights.
+// H, ping, pong (3 x NP^2 x 16 B) + the control weights of the next 16 items.
 // ---------------------------------------------------------------------------------------------
+constexpr int EXPM_WB = 16;                      // items whose control weights are evaluated together
+__host__ __device__ inline size_t expm_item_bytes(int mat, int K) {
+  return (size_t)3 * mat * sizeof(cplx) + (((size_t)EXPM_WB * (K + 1) * sizeof(double) + 15) & ~(size_t)15);
+}
+
 template <int NP, int RB, int CB>
 __global__ void __launch_bounds__(MT<NP, RB, CB>::WARPS == 1 ? 128 : MT<NP, RB, CB>::THREADS)
 k_expm_mma(QocParams p) {
@@ -421,33 +426,57 @@ k_expm_mma(QocParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = WARPS == 1 ? 0 : (threadIdx.x >> 5);
   const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
-  const size_t item_bytes = (size_t)3 * T_::MAT * sizeof(cplx) + 32 * sizeof(double);
+  const int n = p.n, K = p.K, T = p.T, nn = n * n;
+  const size_t item_bytes = expm_item_bytes(T_::MAT, K);
   cplx* Hs = reinterpret_cast<cplx*>(smem_raw + slot * item_bytes);
   cplx* buf1 = Hs + T_::MAT;
   cplx* buf2 = buf1 + T_::MAT;
-  double* wts = reinterpret_cast<double*>(buf2 + T_::MAT);
-  const int n = p.n, K = p.K, T = p.T, nn = n * n;
+  double* wtab = reinterpret_cast<double*>(buf2 + T_::MAT);       // [EXPM_WB][K+1] control weights of the next items
   const int ksteps = (n + 3) >> 2;
   const long long items = (long long)p.B * T;
+  const bool small = items < 0x7fffffffLL;                        // 32-bit index arithmetic (the common case)
   cplx* Pout = reinterpret_cast<cplx*>(p.P);
   const int g = lane >> 2, q = lane & 3;
+  const int pat_n = p.pat_n;
 
   for (int i = gt; i < 3 * T_::MAT; i += G) Hs[i] = make_double2(0.0, 0.0);   // padding stays zero forever
   item_sync<WARPS>();
 
-  for (long long item = (long long)blockIdx.x * ipc + slot; item < items; item += (long long)gridDim.x * ipc) {
-    const int b = (int)(item / T), t = (int)(item % T);
-    // u_k(t)/2^s with u_k = maxA_k sin(base) (tensorflow_state.py:31,176-178); weight 0 = drift
-    if (gt == 0) wts[0] = p.inv2s;
-    if (gt >= 1 && gt <= K) wts[gt] = p.maxA[gt - 1] * sin(p.base[((size_t)b * K + gt - 1) * T + t]) * p.inv2s;
-    item_sync<WARPS>();
-    // H assembly over the union sparsity pattern of A_0..A_K (entries outside it are never written)
-    for (int e = gt; e < p.pat_n; e += G) {
-      const int rc = p.pat_rc[e];
-      const cplx* cf = p.pat_coef + (size_t)e * (K + 1);
+  const long long stride = (long long)gridDim.x * ipc;
+  int it = 0;
+  for (long long item = (long long)blockIdx.x * ipc + slot; item < items; item += stride, ++it) {
+    int b, t;
+    if (small) { b = (int)((unsigned)item / (unsigned)T); t = (int)item - b * T; }
+    else { b = (int)(item / T); t = (int)(item % T); }
+    // u_k(t)/2^s with u_k = maxA_k sin(base) (tensorflow_state.py:31,176-178); weight 0 = drift.
+    // The sines of the next EXPM_WB items of this CTA are evaluated together by all its threads
+    // (K of 64 lanes busy per item otherwise: ~1100 cycles of an item's ~50 000).
+    const int wslot = it % EXPM_WB;
+    if (wslot == 0) {
+      for (int idx = gt; idx < EXPM_WB * (K + 1); idx += G) {
+        const int j = idx / (K + 1), k = idx - j * (K + 1);
+        const long long itj = item + (long long)j * stride;
+        double w = p.inv2s;
+        if (k > 0) {
+          w = 0.0;
+          if (itj < items) {
+            const int bj = (int)(itj / T), tj = (int)(itj - (long long)bj * T);
+            w = p.maxA[k - 1] * sin(p.base[((size_t)bj * K + k - 1) * T + tj]) * p.inv2s;
+          }
+        }
+        wtab[idx] = w;
+      }
+      item_sync<WARPS>();
+    }
+    const double* wts = wtab + wslot * (K + 1);
+    // H assembly over the union sparsity pattern of A_0..A_K (entries outside it are never written);
+    // coefficients are k-major ([K+1][pat_n]: coalesced).  Keeping several entries per thread in flight was
+    // tried and lost: the extra live registers spill in this 255-register kernel (5.41 -> 5.59 ms).
+    for (int e = gt; e < pat_n; e += G) {
+      const int rc = __ldg(p.pat_rc + e);
       double hx = 0.0, hy = 0.0;
       for (int k = 0; k <= K; ++k) {
-        const cplx a = cf[k];
+        const cplx a = __ldg(p.pat_coef + (size_t)k * pat_n + e);
         const double w = wts[k];
         hx = fma(w, a.x, hx); hy = fma(w, a.y, hy);
       }
@@ -769,7 +798,7 @@ cudaError_t launch_expm(const QocParams& p, int sm_count, cudaStream_t st) {
   typedef MT<NP, RB, CB> T_;
   const int ipc = T_::WARPS == 1 ? 4 : 1;
   const int threads = T_::WARPS == 1 ? 128 : T_::THREADS;
-  const size_t smem = ((size_t)3 * T_::MAT * sizeof(cplx) + 32 * sizeof(double)) * ipc;
+  const size_t smem = expm_item_bytes(T_::MAT, p.K) * ipc;
   cudaError_t e = cudaFuncSetAttribute(k_expm_mma<NP, RB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;

@@ -48,7 +48,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("QOC_B200_LIB") or LIB_PATH        # QOC_B200_LIB: A/B runs against another build
     if not os.path.exists(path):
         raise QocError("%s not found: build it with `python __graft_entry__.py` (or "
                        "quantum-optimal-control_b200/build.py); there is no CPU fallback" % path)
