@@ -253,12 +253,12 @@ def run_ours(args):
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))      # host Adam: share the cores between ranks
     hbase = eng.host_buffers()['base']                      # pinned host weights, updated in place by the host Adam
     hbase[...] = np.asarray(sp.ops_weight_base, dtype=np.float64)
-    hadam = HostAdam(hbase.shape)
-    for _ in range(max(1, min(args.warmup, 2))):
+    hadam = HostAdam(hbase.shape, threads=max(1, min(4, (os.cpu_count() or 1) // max(world, 1))))
+    for _ in range(max(3, min(args.warmup, 5))):
         o = eng.value_and_grad_host(hbase, copy=False)
         hadam.step(hbase, o['grad'], lr)
     barrier()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 50))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         o = eng.value_and_grad_host(hbase, copy=False)      # pinned H2D of the weights, kernels, D2H of grad + losses

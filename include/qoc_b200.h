@@ -177,6 +177,14 @@ int qoc_poll_error(qoc_handle_t h, void* stream);
 int qoc_set_profiling(qoc_handle_t h, int enable);
 int qoc_kernel_times_ms(qoc_handle_t h, float* ms_out /* [QOC_NUM_KERNELS] */);
 
+/* TF-1 AdamOptimizer apply step (tf.train.AdamOptimizer as constructed at core/tensorflow_state.py:345, applied by
+ * run_session.py:66-67) on HOST arrays of `count` doubles, one fused multi-threaded pass:
+ *   m <- beta1 m + (1-beta1) g;  v <- beta2 v + (1-beta2) g^2;  theta <- theta - lr_t m / (sqrt(v) + eps)
+ * with lr_t = lr sqrt(1-beta2^t) / (1-beta1^t) formed by the caller.  Companion of qoc_value_and_grad_host for
+ * callers that keep the weights on the host; needs no GPU. */
+int qoc_adam_host(double* theta, const double* grad, double* m, double* v, size_t count, double lr_t, double beta1,
+                  double beta2, double eps, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libqoc_b200.so")
 SOURCES = ["qoc_mma_f64.cu", "qoc_large_f64.cu", "qoc_tc_tf32.cu", "qoc_sweeps.cu", "qoc_vecsweep.cu", "qoc_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "--use_fast_math=false"]
 
 
 def _nvcc():
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs
+    cmd = [_nvcc(), "-shared", "-Xcompiler", "-fopenmp", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

@@ -584,4 +584,30 @@ int qoc_kernel_times_ms(qoc_handle_t h, float* ms_out) {
   return QOC_OK;
 }
 
+// TF-1 AdamOptimizer apply step on HOST arrays in one fused, multi-threaded pass (the optimiser of callers that keep the
+// weights on the host and use the *_host entry points; init_optimizer / apply_gradients, core/tensorflow_state.py:342-356):
+//   m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g^2;  theta <- theta - lr_t m / (sqrt(v) + eps)
+// lr_t = lr sqrt(1-b2^t)/(1-b1^t) is formed by the caller.  No FMA contraction, so the result equals the five-pass
+// NumPy / torch formulation to the last bit or two.
+int qoc_adam_host(double* theta, const double* grad, double* m, double* v, size_t count, double lr_t, double beta1,
+                  double beta2, double eps, int threads) {
+  if (!theta || !grad || !m || !v) return QOC_EINVAL;
+  if (threads < 1) threads = 1;
+  const double c1 = 1.0 - beta1, c2 = 1.0 - beta2;
+  const long long n = (long long)count;
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (long long i = 0; i < n; ++i) {
+    const double g = grad[i];
+    const double a = beta1 * m[i], bb = c1 * g;
+    const double mi = a + bb;
+    const double c = beta2 * v[i], gg = g * g, dd = c2 * gg;
+    const double vi = c + dd;
+    m[i] = mi; v[i] = vi;
+    const double den = sqrt(vi) + eps;
+    const double q = mi / den, u = lr_t * q;
+    theta[i] = theta[i] - u;
+  }
+  return QOC_OK;
+}
+
 }  // extern "C"

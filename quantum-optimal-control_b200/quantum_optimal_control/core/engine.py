@@ -19,7 +19,7 @@ _DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF
 SYMBOLS = ["qoc_abi_version", "qoc_create", "qoc_destroy", "qoc_last_error", "qoc_workspace_bytes",
            "qoc_set_workspace", "qoc_set_problem", "qoc_set_regularizers", "qoc_value_and_grad", "qoc_evolve",
            "qoc_value_and_grad_host", "qoc_evolve_host", "qoc_debug_propagators", "qoc_launch_count", "qoc_set_profiling",
-           "qoc_kernel_times_ms", "qoc_poll_error", "qoc_set_forbid_basis", "qoc_batch_chunk"]
+           "qoc_kernel_times_ms", "qoc_poll_error", "qoc_set_forbid_basis", "qoc_batch_chunk", "qoc_adam_host"]
 
 
 class QocDims(C.Structure):
@@ -75,6 +75,7 @@ def load_library(path=None):
     lib.qoc_set_forbid_basis.argtypes = [vp, dp, vp]
     lib.qoc_set_profiling.argtypes = [vp, C.c_int]
     lib.qoc_kernel_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.qoc_adam_host.argtypes = [dp, dp, dp, dp, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
     for fn in SYMBOLS:
         if fn not in ("qoc_last_error", "qoc_launch_count", "qoc_abi_version"):
             getattr(lib, fn).restype = C.c_int

@@ -42,29 +42,33 @@ class TF1AdamState:
 class TF1AdamHost:
     """Host twin of :class:`TF1AdamState` for callers that keep the weights on the host and go through the
     host-buffer C-ABI entry point (``GrapeEngine.value_and_grad_host``).  ``theta`` / ``grad`` are NumPy arrays
-    (typically the pinned ``host_buffers()``); the update runs in place through torch-CPU views of them so it is
-    multi-threaded and allocation-free."""
+    (typically the pinned ``host_buffers()``); the update is ONE fused multi-threaded pass in the library
+    (``qoc_adam_host``) -- five torch passes spent more time waking their thread team after the GPU wait than on
+    the arithmetic."""
 
-    def __init__(self, shape, beta1=0.9, beta2=0.999, eps=1e-8):
-        import torch
-        self.torch = torch
-        self.m = torch.zeros(tuple(shape), dtype=torch.float64)
-        self.v = torch.zeros(tuple(shape), dtype=torch.float64)
-        self.tmp = torch.empty(tuple(shape), dtype=torch.float64)
+    def __init__(self, shape, beta1=0.9, beta2=0.999, eps=1e-8, threads=None):
+        import os
+        from .engine import load_library
+        self.lib = load_library()
+        self.m = np.zeros(tuple(shape), dtype=np.float64)
+        self.v = np.zeros(tuple(shape), dtype=np.float64)
         self.t = 0
         self.b1, self.b2, self.eps = beta1, beta2, eps
+        # 4 threads: the gradient was just written by DMA and is cold in every cache; more threads only add wake-up
+        # and cross-socket traffic (tools/e2e_breakdown.py: 1/2/4/8/16 threads -> 8.83/8.15/7.99/8.10/8.31 ms per C2 step)
+        self.threads = int(threads) if threads else max(1, min(4, (os.cpu_count() or 1)))
 
     def step(self, theta, grad, lr):
-        torch = self.torch
+        import ctypes as C
         self.t += 1
         lr_t = lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
-        th = torch.from_numpy(theta)
-        g = torch.from_numpy(np.ascontiguousarray(grad))
-        self.m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
-        self.v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
-        torch.sqrt(self.v, out=self.tmp)
-        self.tmp.add_(self.eps)
-        th.addcdiv_(self.m, self.tmp, value=-lr_t)
+        g = np.ascontiguousarray(grad, dtype=np.float64)
+        assert theta.dtype == np.float64 and theta.flags.c_contiguous and theta.shape == self.m.shape == g.shape
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = self.lib.qoc_adam_host(p(theta), p(g), p(self.m), p(self.v), C.c_size_t(theta.size), float(lr_t),
+                                    float(self.b1), float(self.b2), float(self.eps), int(self.threads))
+        if rc:
+            raise RuntimeError("qoc_adam_host failed (%d)" % rc)
         return theta
 
 
