@@ -35,7 +35,7 @@ static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
   L.st_grad = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_out = off; off += align_up((size_t)d.B * 4 * sizeof(double));
   L.seg = off;                                   // segment products of the re-associated U_final chain (n <= 64, fp64)
-  if (d.n <= 64 && d.dtype == QOC_F64)
+  if (d.n <= 64)
     off += align_up((size_t)Bc * ((d.T + QOC_SEG_LEN - 1) / QOC_SEG_LEN) * nn * sizeof(cplx));
   L.scratch = off;
   if (d.n > 64) off += align_up(qoc_large_scratch_elems(d.n, Bc, sm_count) * sizeof(cplx));
@@ -349,7 +349,8 @@ static QocParams chunk_params(const QocParams& p, const qoc_dims_t& d, int b0, i
 // beside it.  QOC_B200_NO_VEC_SWEEP=1 restores the single-stream chain.
 static bool use_vec_sweeps(qoc_handle_t h, const QocParams& p) {
   const bool off = getenv("QOC_B200_NO_VEC_SWEEP") != nullptr;     // read per call: tests flip it
-  return !off && h->d.dtype == QOC_F64 && h->d.n <= 64 && 2 * h->d.m < h->NP && qoc_vec_sweep_supported(p);
+  if (off || 2 * h->d.m >= h->NP || !qoc_vec_sweep_supported(p)) return false;
+  return h->d.dtype == QOC_F64 ? h->d.n <= 64 : h->d.n <= 32;      // QOC_TF32X3: fp32 32 x 32 propagator tiles
 }
 
 // the caller's stream waits for the critical-path branch
@@ -370,11 +371,13 @@ static int launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   int L = QOC_SEG_LEN;
   if (getenv("QOC_B200_SEG_LEN")) { L = atoi(getenv("QOC_B200_SEG_LEN")); if (L < QOC_SEG_LEN) L = QOC_SEG_LEN; }   // experiments: longer segments only
   const int S = (p.T + L - 1) / L;
+  bool pf32 = h->d.dtype != QOC_F64;                // fp32 propagator tiles (tcgen05 path); the segment matrices are fp64
   if (S >= 4) {
-    CUDA_TRY(h, qoc_launch_segprod_f64(p, h->NP, L, S, h->seg, st, &h->launches));
+    CUDA_TRY(h, qoc_launch_segprod_f64(p, h->NP, pf32 ? 1 : 0, L, S, h->seg, st, &h->launches));
     q.P = h->seg; q.T = S;
+    pf32 = false;
   }
-  CUDA_TRY(h, qoc_launch_chain_f64(q, h->NP, 0, st, &h->launches));
+  CUDA_TRY(h, qoc_launch_chain_f64(q, h->NP, pf32 ? 1 : 0, st, &h->launches));
   return QOC_OK;
 }
 
@@ -400,7 +403,7 @@ static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
       h->work = h->hi;
       h->hi_pending = true;
     }
-    CUDA_TRY(h, qoc_launch_vec_sweep(p, 0, h->work, &h->launches));   // critical path first: psi(t)
+    CUDA_TRY(h, qoc_launch_vec_sweep(p, 0, h->d.dtype != QOC_F64, h->work, &h->launches));   // critical path first: psi(t)
     if (!p.state_transfer && xmode != 0 && (rc = launch_xchain(h, p, st))) return rc;
   } else CUDA_TRY(h, qoc_launch_chain_f64(p, h->NP, h->d.dtype != QOC_F64, st, &h->launches));
   cudaStream_t ws = h->work;
@@ -433,7 +436,7 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
     const bool dense_A = (double)h->nnz >= 0.25 * (double)h->d.K * h->d.n * h->d.n;
     if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, ws, &h->launches));
     else if (dense_m) CUDA_TRY(h, qoc_launch_costate_mma(p, h->NP, ws, &h->launches));
-    else if (use_vec_sweeps(h, p)) CUDA_TRY(h, qoc_launch_vec_sweep(p, 1, ws, &h->launches));
+    else if (use_vec_sweeps(h, p)) CUDA_TRY(h, qoc_launch_vec_sweep(p, 1, h->d.dtype != QOC_F64, ws, &h->launches));
     else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, ws, &h->launches));
     if ((rc = prof_mark(h, 4, ws))) return rc;
     if (dense_m && dense_A) CUDA_TRY(h, qoc_launch_grad_mma(p, h->NP, h->sm_count, ws, &h->launches));

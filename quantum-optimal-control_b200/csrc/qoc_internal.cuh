@@ -88,9 +88,10 @@ struct qoc_handle_s {
 // kernel launchers (qoc_mma_f64.cu, qoc_sweeps.cu); return cudaError_t, bump *launches
 cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_chain_f64(const QocParams& p, int NP, int p_is_f32, cudaStream_t st, int64_t* launches);
-cudaError_t qoc_launch_segprod_f64(const QocParams& p, int NP, int L, int S, cplx* seg_out, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_segprod_f64(const QocParams& p, int NP, int p_is_f32, int L, int S, cplx* seg_out, cudaStream_t st,
+                                   int64_t* launches);
 bool qoc_vec_sweep_supported(const QocParams& p);
-cudaError_t qoc_launch_vec_sweep(const QocParams& p, int reverse, cudaStream_t st, int64_t* launches);
+cudaError_t qoc_launch_vec_sweep(const QocParams& p, int reverse, int p_is_f32, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_expm_tc32(const QocParams& p, int sm_count, int* err_flag, cudaStream_t st, int64_t* launches);
 size_t qoc_large_scratch_elems(int n, int B, int sm_count);
 cudaError_t qoc_launch_expm_large(const QocParams& p, int sm_count, void* scratch, cudaStream_t st, int64_t* launches);

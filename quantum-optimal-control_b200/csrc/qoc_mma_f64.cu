@@ -725,13 +725,16 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
 // One short-lived CTA per segment (so that higher-priority sweep CTAs get SM slots as segments
 // retire); X is updated in place, P_t double-buffered with cp.async.
 // ---------------------------------------------------------------------------------------------
-template <int NP, int RB, int CB>
+// PF32: the propagators are the tcgen05 path's fp32 planar padded [2][32][32] tiles; they are staged raw (double
+// buffered) and widened into the one swizzled operand buffer each step.
+template <int NP, int RB, int CB, bool PF32>
 __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p, int L, int S, cplx* __restrict__ seg_out) {
   typedef MT<NP, RB, CB> T_;
   constexpr int G = T_::THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* Xb = reinterpret_cast<cplx*>(smem_raw);            // [MAT]
-  cplx* Pb = Xb + T_::MAT;                                 // [2][MAT]
+  cplx* Pb = Xb + T_::MAT;                                 // [2][MAT]   (PF32: [1][MAT] + raw staging [2][2048] floats)
+  float* Pstage = reinterpret_cast<float*>(Pb + T_::MAT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb0 = (warp / T_::WC) * RB, cb0 = (warp % T_::WC) * CB;
   const int n = p.n, T = p.T, nn = n * n;
@@ -741,30 +744,59 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
   const int seg = blockIdx.x / p.B, b = blockIdx.x - seg * p.B;
   const int t0 = seg * L, len = min(L, T - t0);
   const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + ((size_t)b * T + t0) * nn;
+  const float* Pgf = reinterpret_cast<const float*>(p.P) + ((size_t)b * T + t0) * 2048;
 
   for (int i = tid; i < 3 * T_::MAT; i += G) Xb[i] = make_double2(0.0, 0.0);   // padding rows / columns stay zero
   __syncthreads();
   const int dr = G / n, dc = G - dr * n, r_first = tid / n, c_first = tid - r_first * n;
-  auto fetch = [&](int l, cplx* dst) {                     // P_{t0+l} -> swizzled operand buffer
+  auto fetch = [&](int l, cplx* dst) {                     // P_{t0+l} -> swizzled operand buffer (PF32: raw staging)
     if (l < len) {
-      const cplx* src = Pg + (size_t)l * nn + tid;
-      int r = r_first, c = c_first;
-      for (int idx = tid; idx < nn; idx += G, src += G) {
-        cp_async16(dst + swz<NP>(r, c), src);
-        r += dr; c += dc;
-        if (c >= n) { c -= n; ++r; }
+      if (PF32) {
+        const float* src = Pgf + (size_t)l * 2048;
+        float* stg = Pstage + (l & 1) * 2048;
+        for (int c = tid; c < 512; c += G) cp_async16(stg + 4 * c, src + 4 * c);
+      } else {
+        const cplx* src = Pg + (size_t)l * nn + tid;
+        int r = r_first, c = c_first;
+        for (int idx = tid; idx < nn; idx += G, src += G) {
+          cp_async16(dst + swz<NP>(r, c), src);
+          r += dr; c += dc;
+          if (c >= n) { c -= n; ++r; }
+        }
       }
     }
     cp_async_commit();
   };
+  auto widen = [&](int l, cplx* dst) {                     // PF32: raw tile of step l -> swizzled double2 operand
+    const float* stg = Pstage + (l & 1) * 2048;
+    int r = r_first, c = c_first;
+    for (int idx = tid; idx < nn; idx += G) {
+      dst[swz<NP>(r, c)] = make_double2((double)stg[r * 32 + c], (double)stg[1024 + r * 32 + c]);
+      r += dr; c += dc;
+      if (c >= n) { c -= n; ++r; }
+    }
+  };
   fetch(0, Xb);
   fetch(1, Pb);
-  for (int l = 1; l < len; ++l) {
-    fetch(l + 1, Pb + (l & 1) * T_::MAT);                  // the buffer step l-1 used
+  if (PF32) {
     cp_async_wait<1>();
-    __syncthreads();                                       // P_{t0+l} landed; X complete
+    __syncthreads();
+    widen(0, Xb);
+  }
+  for (int l = 1; l < len; ++l) {
+    if (PF32) {
+      cp_async_wait<0>();
+      __syncthreads();                                     // raw P_{t0+l} landed; X complete; Pb free (step l-1 done)
+      widen(l, Pb);
+      fetch(l + 1, nullptr);                               // staging half (l+1)&1 == (l-1)&1 was consumed a step ago
+      __syncthreads();
+    } else {
+      fetch(l + 1, Pb + (l & 1) * T_::MAT);                // the buffer step l-1 used
+      cp_async_wait<1>();
+      __syncthreads();                                     // P_{t0+l} landed; X complete
+    }
     double cr[RB][CB][2], ci[RB][CB][2];
-    mma_gemm<NP, RB, CB>(Pb + ((l - 1) & 1) * T_::MAT, Xb, cr, ci, rb0, cb0, ksteps, lane);
+    mma_gemm<NP, RB, CB>(PF32 ? Pb : Pb + ((l - 1) & 1) * T_::MAT, Xb, cr, ci, rb0, cb0, ksteps, lane);
     __syncthreads();                                       // in-place update: every warp has finished reading X
     store_tile<NP, RB, CB>(Xb, cr, ci, rb0, cb0, lane);
   }
@@ -781,15 +813,15 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
   }
 }
 
-template <int NP, int RB, int CB>
+template <int NP, int RB, int CB, bool PF32 = false>
 cudaError_t launch_segprod(const QocParams& p, int L, int S, cplx* seg_out, cudaStream_t st) {
   typedef MT<NP, RB, CB> T_;
-  const size_t smem = (size_t)3 * T_::MAT * sizeof(cplx);
-  cudaError_t e = cudaFuncSetAttribute(k_segprod<NP, RB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = PF32 ? (size_t)2 * T_::MAT * sizeof(cplx) + 2 * 2048 * sizeof(float) : (size_t)3 * T_::MAT * sizeof(cplx);
+  cudaError_t e = cudaFuncSetAttribute(k_segprod<NP, RB, CB, PF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_segprod<NP, RB, CB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_segprod<NP, RB, CB, PF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  k_segprod<NP, RB, CB><<<(unsigned)((size_t)p.B * S), T_::THREADS, smem, st>>>(p, L, S, seg_out);
+  k_segprod<NP, RB, CB, PF32><<<(unsigned)((size_t)p.B * S), T_::THREADS, smem, st>>>(p, L, S, seg_out);
   return cudaGetLastError();
 }
 
@@ -1128,8 +1160,18 @@ cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaSt
   return cudaErrorInvalidValue;
 }
 
-cudaError_t qoc_launch_segprod_f64(const QocParams& p, int NP, int L, int S, cplx* seg_out, cudaStream_t st, int64_t* launches) {
+cudaError_t qoc_launch_segprod_f64(const QocParams& p, int NP, int p_is_f32, int L, int S, cplx* seg_out, cudaStream_t st,
+                                   int64_t* launches) {
   ++*launches;
+  if (p_is_f32) {                                     // tcgen05 path: n <= 32
+    switch (NP) {
+      case 8: return launch_segprod<8, 1, 1, true>(p, L, S, seg_out, st);
+      case 16: return launch_segprod<16, 2, 2, true>(p, L, S, seg_out, st);
+      case 24: return launch_segprod<24, 1, 3, true>(p, L, S, seg_out, st);
+      case 32: return launch_segprod<32, 2, 4, true>(p, L, S, seg_out, st);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (NP) {
     case 8: return launch_segprod<8, 1, 1>(p, L, S, seg_out, st);
     case 16: return launch_segprod<16, 2, 2>(p, L, S, seg_out, st);

@@ -61,18 +61,23 @@ struct SweepShape {
 };
 
 template <int NR, int NST, int CPW = 2>
-SweepShape sweep_shape(int n, int m) {
+SweepShape sweep_shape(int n, int m, bool pf32 = false) {
   SweepShape s;
   s.npairs = (m + CPW - 1) / CPW;                // column groups (CPW columns per warp)
   s.cp = s.npairs < 4 ? s.npairs : 4;
   const int mp = CPW * s.npairs;                 // columns rounded up to whole groups
   // ring (+ slack for the padded lanes of the last row) + vectors [2][mp][VL] + partials [WK][mp][VL] + mbarriers
-  s.smem = ((size_t)NST * n * n + 64 + (size_t)(2 + WK) * mp * NR * 32) * sizeof(cplx) + 8 * NST;
+  s.smem = ((size_t)NST * (pf32 ? 512 : n * n) + 64 + (size_t)(2 + WK) * mp * NR * 32) * sizeof(cplx) + 8 * NST;
   return s;
 }
 
-template <bool REV, int NR, int NST, int CPW>
+// PF32: the propagators are the tcgen05 path's fp32 planar padded [2][32][32] tiles (csrc/qoc_tc_tf32.cu), 8 KB per
+// step; they are widened to double on the fly.  The forward sweep reads tile COLUMNS (lane stride 32 floats = one bank),
+// so there every lane walks its warp's k-slice in a rotated order, k = 8 wk + ((i + lane) & 7): 4-way instead of 32-way
+// bank conflicts, no transposition.
+template <bool REV, int NR, int NST, int CPW, bool PF32>
 __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
+  static_assert(!PF32 || NR == 1, "fp32 tiles are 32 x 32");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int VL = NR * 32;
   constexpr int KI = VL / WK;                    // k iterations per warp (upper bound, predicated on k < n)
@@ -81,15 +86,16 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
   const int wk = warp % WK, cp0 = warp / WK;
   const int npairs = (m + CPW - 1) / CPW, mp = CPW * npairs;
   const int b = blockIdx.x;
+  const int stage_elems = PF32 ? 512 : nn;                              // in cplx units (PF32: 2048 floats)
   cplx* ring = reinterpret_cast<cplx*>(smem_raw);                       // [NST][n][n] row-major, as in HBM
-  cplx* vecs = ring + (size_t)NST * nn + 64;                            // [2][mp][VL]
+  cplx* vecs = ring + (size_t)NST * stage_elems + 64;                   // [2][mp][VL]
   cplx* part = vecs + (size_t)2 * mp * VL;                              // [WK][mp][VL]
   uint64_t* full = reinterpret_cast<uint64_t*>(part + (size_t)WK * mp * VL);   // [NST]
-  const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * nn;
+  const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * stage_elems;
   cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
   cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn;
   const int nsteps = REV ? T - 1 : T;
-  const uint32_t stage_bytes = (uint32_t)nn * sizeof(cplx);
+  const uint32_t stage_bytes = (uint32_t)stage_elems * sizeof(cplx);
 
   if (tid == 0) {
 #pragma unroll
@@ -104,7 +110,7 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
       uint64_t* bar = &full[step % NST];
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage (ordered by the barrier) before the async write
       mbar_expect_tx(bar, stage_bytes);
-      bulk_g2s(ring + (size_t)(step % NST) * nn, Pg + (size_t)t * nn, stage_bytes, bar);
+      bulk_g2s(ring + (size_t)(step % NST) * stage_elems, Pg + (size_t)t * stage_elems, stage_bytes, bar);
     }
   };
   if (tid == 0) {
@@ -159,14 +165,22 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
 
   // loop-invariant element offsets of the k loop: reverse P[k][l] -> k*n + l, forward P[l][k] -> l*n + k;
   // rows / columns beyond n are clamped (their products are discarded or multiplied by v = 0)
-  int moff[KI][NR];
+  int moff[KI][NR], kidx[KI];
 #pragma unroll
-  for (int i = 0; i < KI; ++i)
+  for (int i = 0; i < KI; ++i) {
+    if (PF32) {                                  // contiguous k-slices; forward: rotated per lane (see above)
+      const int k = 8 * wk + (REV ? i : ((i + lane) & 7));
+      kidx[i] = k;
+      moff[i][0] = REV ? k * 32 + lane : lane * 32 + k;                 // float index into the Re plane
+    } else {
+      kidx[i] = wk + WK * i;
 #pragma unroll
-    for (int rr = 0; rr < NR; ++rr) {
-      const int k = min(wk + WK * i, n - 1), l = min(lane + 32 * rr, n - 1);
-      moff[i][rr] = REV ? k * n + l : l * n + k;
+      for (int rr = 0; rr < NR; ++rr) {
+        const int k = min(wk + WK * i, n - 1), l = min(lane + 32 * rr, n - 1);
+        moff[i][rr] = REV ? k * n + l : l * n + k;
+      }
     }
+  }
   // the element this thread finalises
   const int fj = tid / VL, fr = tid - fj * VL;
   const bool fin = tid < mp * VL, fval = fin && fj < m && fr < n;
@@ -184,9 +198,10 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
       const uint32_t parity = (uint32_t)(step / NST) & 1u;
       while (!mbar_try_wait(bar, parity)) {}
     }
-    const cplx* M = ring + (size_t)(step % NST) * nn;
+    const cplx* M = ring + (size_t)(step % NST) * stage_elems;
+    const float* Mf = reinterpret_cast<const float*>(M);
     for (int pr = cp0; pr < npairs; pr += CP) {
-      const cplx* va = vecs + ((size_t)cur * mp + CPW * pr) * VL + wk;
+      const cplx* va = vecs + ((size_t)cur * mp + CPW * pr) * VL;
       const cplx* vb = va + (CPW - 1) * VL;
       double a0[NR][4], a1[NR][4];               // partial sums  xx, yy, xy, yx
 #pragma unroll
@@ -195,11 +210,13 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
         for (int e = 0; e < 4; ++e) a0[rr][e] = a1[rr][e] = 0.0;
 #pragma unroll
       for (int i = 0; i < KI; ++i) {
-        if (wk + WK * i < n) {                   // warp-uniform
-          const cplx x = va[WK * i], y = CPW == 2 ? vb[WK * i] : x;
+        if (PF32 || wk + WK * i < n) {           // warp-uniform (fp32 tiles are zero-padded: no predicate)
+          const cplx x = va[kidx[i]], y = CPW == 2 ? vb[kidx[i]] : x;
 #pragma unroll
           for (int rr = 0; rr < NR; ++rr) {
-            const cplx e = M[moff[i][rr]];
+            cplx e;
+            if (PF32) e = make_double2((double)Mf[moff[i][0]], (double)Mf[1024 + moff[i][0]]);
+            else e = M[moff[i][rr]];
             a0[rr][0] = fma(e.x, x.x, a0[rr][0]); a0[rr][1] = fma(e.y, x.y, a0[rr][1]);
             a0[rr][2] = fma(e.x, x.y, a0[rr][2]); a0[rr][3] = fma(e.y, x.x, a0[rr][3]);
             if (CPW == 2) {
@@ -245,16 +262,16 @@ __global__ void __launch_bounds__(512) k_vec_sweep(QocParams p, int CP) {
   }
 }
 
-template <bool REV, int NR, int NST, int CPW>
+template <bool REV, int NR, int NST, int CPW, bool PF32>
 cudaError_t launch_cpw(const QocParams& p, cudaStream_t st) {
-  const SweepShape s = sweep_shape<NR, NST, CPW>(p.n, p.m);
-  cudaError_t e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+  const SweepShape s = sweep_shape<NR, NST, CPW>(p.n, p.m, PF32);
+  cudaError_t e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST, CPW, PF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
   if (e != cudaSuccess) return e;
   // same (maximal) shared-memory carve-out as the kernels it runs beside: CTAs of kernels that ask
   // for different carve-outs cannot share an SM
-  e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST, CPW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_vec_sweep<REV, NR, NST, CPW, PF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  k_vec_sweep<REV, NR, NST, CPW><<<p.B, 32 * WK * s.cp, s.smem, st>>>(p, s.cp);
+  k_vec_sweep<REV, NR, NST, CPW, PF32><<<p.B, 32 * WK * s.cp, s.smem, st>>>(p, s.cp);
   return cudaGetLastError();
 }
 
@@ -264,7 +281,7 @@ template <bool REV, int NR, int NST>
 cudaError_t launch(const QocParams& p, cudaStream_t st) {
   static const int force = getenv("QOC_B200_SWEEP_CPW") ? atoi(getenv("QOC_B200_SWEEP_CPW")) : 0;
   const bool one = force == 1;
-  return one ? launch_cpw<REV, NR, NST, 1>(p, st) : launch_cpw<REV, NR, NST, 2>(p, st);
+  return one ? launch_cpw<REV, NR, NST, 1, false>(p, st) : launch_cpw<REV, NR, NST, 2, false>(p, st);
 }
 
 }  // namespace
@@ -276,9 +293,10 @@ bool qoc_vec_sweep_supported(const QocParams& p) {
 }
 
 // ring depth: 4 stages when two CTAs of that size still leave an SM room for the U_final branch, else 3
-cudaError_t qoc_launch_vec_sweep(const QocParams& p, int reverse, cudaStream_t st, int64_t* launches) {
-  if (!qoc_vec_sweep_supported(p)) return cudaErrorNotSupported;
+cudaError_t qoc_launch_vec_sweep(const QocParams& p, int reverse, int p_is_f32, cudaStream_t st, int64_t* launches) {
+  if (!qoc_vec_sweep_supported(p) || (p_is_f32 && p.n > 32)) return cudaErrorNotSupported;
   ++*launches;
+  if (p_is_f32) return reverse ? launch_cpw<true, 1, 4, 2, true>(p, st) : launch_cpw<false, 1, 4, 2, true>(p, st);
   static const int force = getenv("QOC_B200_SWEEP_STAGES") ? atoi(getenv("QOC_B200_SWEEP_STAGES")) : 0;
   if (p.n > 32) {
     const bool deep = force ? force >= 4 : sweep_shape<2, 4>(p.n, p.m).smem <= 84 * 1024;

@@ -401,6 +401,34 @@ def test_vec_sweep_path_matches_oracle_and_single_stream_path(name, built_lib, m
     eng.close()
 
 
+@pytest.mark.parametrize("name", ['c2_T100_regs', 'c2_T67'])
+def test_tf32x3_few_state_path_equals_single_stream_path(name, built_lib, monkeypatch):
+    """tcgen05 path: both tails consume the SAME fp32 propagator tiles (widened to double), so the TMA-ring sweeps +
+    segment products must agree with the single-stream chain / scalar costate to fp64 rounding."""
+    fn, over, B = SWEEP_CASES[name]
+    setups, guess, args, kw = make_case(fn(), seed=29, B=B, **over)
+    sp, eng = _engine_tf32(args, kw, guess)
+    base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+    n0 = eng.launch_count
+    out = {k: v.clone() for k, v in eng.value_and_grad(base).items()}
+    n_new = eng.launch_count - n0
+    ev = {k: (None if v is None else v.clone()) for k, v in eng.evolve(base).items()}
+    eng.poll_error()
+    monkeypatch.setenv("QOC_B200_NO_VEC_SWEEP", "1")
+    n0 = eng.launch_count
+    old = {k: v.clone() for k, v in eng.value_and_grad(base).items()}
+    assert eng.launch_count - n0 < n_new
+    ev_old = eng.evolve(base)
+    eng.poll_error()
+    monkeypatch.delenv("QOC_B200_NO_VEC_SWEEP")
+    for k in ('loss', 'reg_loss', 'unitary_scale', 'grad_squared'):
+        assert (out[k] - old[k]).abs().max().item() < 1e-11 * max(1.0, old[k].abs().max().item()), k
+    assert (out['grad'] - old['grad']).abs().max().item() < 1e-11 * old['grad'].abs().max().item()
+    assert (ev['U_final'] - ev_old['U_final']).abs().max().item() < 1e-11
+    assert (ev['inter_vecs'] - ev_old['inter_vecs']).abs().max().item() < 1e-11
+    eng.close()
+
+
 def test_value_and_grad_is_repeatable_across_streams(built_lib):
     """Back-to-back calls reuse the propagator workspace while the high-priority branch of the previous call
     may still be reading it: results must not depend on that (joins are in place)."""
