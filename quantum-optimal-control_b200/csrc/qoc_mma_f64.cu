@@ -8,6 +8,8 @@
 //                (get_matexp / matexp_op, core/tensorflow_state.py:25-46,70-75)
 //   k_chain_mma: b -> X_t = P_t X_{t-1}; psi_j(t+1) = X_t V_j; U_final; unitary_scale
 //                (init_tf_propagator / init_tf_inter_vectors, :204-242)
+//   k_segprod  : (b,seg) -> product of 16 consecutive propagators (U_final re-associated; few-state problems)
+//   k_costate_mma / k_grad_mma: dense-m reverse sweep and control gradient
 //
 // Shared-memory matrix layout: NP x NP complex (double2), row-major, NP = n rounded up to 8, no
 // padding, 16-byte columns XOR-swizzled by row:  phys(r,c) = r*NP + (c ^ sw(r)),
