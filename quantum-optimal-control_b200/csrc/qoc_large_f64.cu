@@ -77,11 +77,12 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
 
   for (int ti = 0; ti < nt; ++ti)
     for (int tj = 0; tj < nt; ++tj) {
-      double cr[RB][CB][2], ci[RB][CB][2];
+      // 3M (Gauss) complex product, as in qoc_mma_f64.cu: cr = Ar Br, t2 = Ai Bi, ci = (Ar+Ai)(Br+Bi); combined below
+      double cr[RB][CB][2], ci[RB][CB][2], t2[RB][CB][2];
 #pragma unroll
       for (int i = 0; i < RB; ++i)
 #pragma unroll
-        for (int j = 0; j < CB; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+        for (int j = 0; j < CB; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = t2[i][j][0] = t2[i][j][1] = 0.0;
       __syncthreads();                                 // previous tile's readers are done with the buffers
       load_tiles(ti, tj, 0, 0);
       for (int kt = 0; kt < nk; ++kt) {
@@ -101,6 +102,11 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
           const int bm = sw_mask(k);
 #pragma unroll
           for (int j = 0; j < CB; ++j) bv[j] = b[k * TS + ((8 * (cb0 + j) + g) ^ bm)];
+          double sa[RB], sb[CB];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) sa[i] = av[i].x + av[i].y;
+#pragma unroll
+          for (int j = 0; j < CB; ++j) sb[j] = bv[j].x + bv[j].y;
 #pragma unroll
           for (int i = 0; i < RB; ++i)
 #pragma unroll
@@ -108,17 +114,11 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
 #pragma unroll
           for (int i = 0; i < RB; ++i)
 #pragma unroll
-            for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], av[i].x, bv[j].y);
-#pragma unroll
-          for (int i = 0; i < RB; ++i) {
-            const double nai = -av[i].y;
-#pragma unroll
-            for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], nai, bv[j].y);
-          }
+            for (int j = 0; j < CB; ++j) dmma(t2[i][j][0], t2[i][j][1], av[i].y, bv[j].y);
 #pragma unroll
           for (int i = 0; i < RB; ++i)
 #pragma unroll
-            for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], av[i].y, bv[j].x);
+            for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], sa[i], sb[j]);
         }
         __syncthreads();                               // buffer (kt & 1) may be refilled two iterations later
       }
@@ -131,7 +131,7 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
           for (int e = 0; e < 2; ++e) {
             const int c = tj * TS + 8 * (cb0 + j) + 2 * q + e;
             if (r < n && c < n) {
-              double vr = cr[i][j][e], vi = ci[i][j][e];
+              double vr = cr[i][j][e] - t2[i][j][e], vi = ci[i][j][e] - cr[i][j][e] - t2[i][j][e];
               if (Hadd) { const cplx h = Hadd[(size_t)r * ldh + c]; vr += c_h * h.x; vi += c_h * h.y; }
               if (r == c) vr += c_id;
               C[(size_t)r * ldc + c] = make_double2(vr, vi);
