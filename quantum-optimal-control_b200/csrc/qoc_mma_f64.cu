@@ -49,13 +49,6 @@ DEVINL void dmma(double& d0, double& d1, const double a, const double b) {
                : "d"(a), "d"(b));
 }
 
-// program-ordered fp64 add (operand sums of the 3M product are scheduled by hand, see mma_gemm)
-DEVINL double dadd_v(const double a, const double b) {
-  double r;
-  asm volatile("add.f64 %0, %1, %2;\n" : "=d"(r) : "d"(a), "d"(b));
-  return r;
-}
-
 template <int NP, int RB, int CB>
 struct MT {
   static constexpr int NBLK = NP / 8;
@@ -101,33 +94,23 @@ DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
   }
   const int bc = 8 * cb0 + g;
 #if QOC_CMUL_3M
-  // software-pipelined by one k-step: the fragments and operand sums of step ks+1 are produced
-  // while the DMMAs of step ks issue, so no DMMA ever waits on a just-issued LDS or DADD
-  cplx a[RB], b[CB];
-  double sa[RB], sb[CB];
-  {
-    const int k = q;
+  // operand sums right where the fragments are loaded: a hand-pipelined variant (sums one k-step ahead) measured
+  // 2.5 % slower in the isolated loop (tools/gemm_loop_probe.cu) and in the kernel, and needs more registers
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k = 4 * ks + q;
+    cplx a[RB], b[CB];
 #pragma unroll
     for (int i = 0; i < RB; ++i) a[i] = A[arow[i] + (k ^ amask[i])];
     const int bm = sw_mask(k);
+    const cplx* Brow = B + k * NP;
 #pragma unroll
-    for (int j = 0; j < CB; ++j) b[j] = B[k * NP + ((bc + 8 * j) ^ bm)];
-  }
+    for (int j = 0; j < CB; ++j) b[j] = Brow[(bc + 8 * j) ^ bm];
+    double sa[RB], sb[CB];
 #pragma unroll
-  for (int i = 0; i < RB; ++i) sa[i] = dadd_v(a[i].x, a[i].y);
+    for (int i = 0; i < RB; ++i) sa[i] = a[i].x + a[i].y;
 #pragma unroll
-  for (int j = 0; j < CB; ++j) sb[j] = dadd_v(b[j].x, b[j].y);
-#pragma unroll 2
-  for (int ks = 0; ks < ksteps; ++ks) {
-    cplx an[RB], bn[CB];
-    {                                           // fragments of the next k-step (the last step re-reads its own)
-      const int k = 4 * min(ks + 1, ksteps - 1) + q;
-#pragma unroll
-      for (int i = 0; i < RB; ++i) an[i] = A[arow[i] + (k ^ amask[i])];
-      const int bm = sw_mask(k);
-#pragma unroll
-      for (int j = 0; j < CB; ++j) bn[j] = B[k * NP + ((bc + 8 * j) ^ bm)];
-    }
+    for (int j = 0; j < CB; ++j) sb[j] = b[j].x + b[j].y;
 #pragma unroll
     for (int i = 0; i < RB; ++i)
 #pragma unroll
@@ -140,10 +123,6 @@ DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
     for (int i = 0; i < RB; ++i)
 #pragma unroll
       for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], sa[i], sb[j]);
-#pragma unroll
-    for (int i = 0; i < RB; ++i) { a[i] = an[i]; sa[i] = dadd_v(an[i].x, an[i].y); }
-#pragma unroll
-    for (int j = 0; j < CB; ++j) { b[j] = bn[j]; sb[j] = dadd_v(bn[j].x, bn[j].y); }
   }
 #else
 #pragma unroll 2
@@ -245,28 +224,19 @@ DEVINL void tri_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
 #pragma unroll
   for (int b = 0; b < H_::NB; ++b) cr[b][0] = cr[b][1] = ci[b][0] = ci[b][1] = 0.0;
 #if QOC_CMUL_3M
-  cplx a0, a1, bv[H_::CA];                     // bv: columns RA..NBLK-1 (superset of RB_..NBLK-1)
-  double s0, s1, sb[H_::CA];
-  {
-    const int k = q, bm = sw_mask(k);
-    a0 = A[ra * NP + (k ^ ma)];
-    a1 = A[rb * NP + (k ^ mb)];
-#pragma unroll
-    for (int j = 0; j < H_::CA; ++j) bv[j] = B[k * NP + ((8 * (H_::RA + j) + g) ^ bm)];
-  }
-  s0 = dadd_v(a0.x, a0.y); s1 = dadd_v(a1.x, a1.y);
-#pragma unroll
-  for (int j = 0; j < H_::CA; ++j) sb[j] = dadd_v(bv[j].x, bv[j].y);
 #pragma unroll 2
   for (int ks = 0; ks < ksteps; ++ks) {
-    cplx a0n, a1n, bn[H_::CA];
-    {
-      const int k = 4 * min(ks + 1, ksteps - 1) + q, bm = sw_mask(k);
-      a0n = A[ra * NP + (k ^ ma)];
-      a1n = A[rb * NP + (k ^ mb)];
+    const int k = 4 * ks + q;
+    const cplx a0 = A[ra * NP + (k ^ ma)], a1 = A[rb * NP + (k ^ mb)];
+    const int bm = sw_mask(k);
+    const cplx* Brow = B + k * NP;
+    cplx bv[H_::CA];                           // columns RA..NBLK-1 (superset of RB_..NBLK-1)
 #pragma unroll
-      for (int j = 0; j < H_::CA; ++j) bn[j] = B[k * NP + ((8 * (H_::RA + j) + g) ^ bm)];
-    }
+    for (int j = 0; j < H_::CA; ++j) bv[j] = Brow[(8 * (H_::RA + j) + g) ^ bm];
+    const double s0 = a0.x + a0.y, s1 = a1.x + a1.y;
+    double sb[H_::CA];
+#pragma unroll
+    for (int j = 0; j < H_::CA; ++j) sb[j] = bv[j].x + bv[j].y;
 #pragma unroll
     for (int j = 0; j < H_::CA; ++j) dmma(cr[j][0], cr[j][1], a0.x, bv[j].x);
 #pragma unroll
@@ -279,10 +249,6 @@ DEVINL void tri_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
     for (int j = 0; j < H_::CA; ++j) dmma(ci[j][0], ci[j][1], s0, sb[j]);
 #pragma unroll
     for (int j = 0; j < H_::CB_; ++j) dmma(ci[H_::CA + j][0], ci[H_::CA + j][1], s1, sb[H_::RB_ - H_::RA + j]);
-    a0 = a0n; a1 = a1n;
-    s0 = dadd_v(a0n.x, a0n.y); s1 = dadd_v(a1n.x, a1n.y);
-#pragma unroll
-    for (int j = 0; j < H_::CA; ++j) { bv[j] = bn[j]; sb[j] = dadd_v(bn[j].x, bn[j].y); }
   }
 #else
 #pragma unroll 2
