@@ -208,3 +208,25 @@ def test_host_adam_matches_tf1_formula():
         a.step(th, g, 0.01 * (i + 1))
         th2 = b.step(th2, g, 0.01 * (i + 1))
     assert np.abs(th - th2).max() < 1e-15
+
+
+def test_qoc_adam_host_c_entry_point():
+    """The fused C entry point itself: odd sizes, more threads than elements, zero elements, null pointers."""
+    import ctypes as C
+    from quantum_optimal_control.core.engine import load_library
+    lib = load_library()
+    rng = np.random.default_rng(3)
+    for count, threads in ((1, 8), (7, 3), (1001, 4), (4096, 1)):
+        th, g = rng.normal(size=count), rng.normal(size=count)
+        m, v = rng.normal(size=count) * 0.1, np.abs(rng.normal(size=count)) * 0.01
+        th0, m0, v0 = th.copy(), m.copy(), v.copy()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert lib.qoc_adam_host(p(th), p(g), p(m), p(v), C.c_size_t(count), 0.02, 0.9, 0.999, 1e-8, threads) == 0
+        m1 = 0.9 * m0 + (1 - 0.9) * g
+        v1 = 0.999 * v0 + (1 - 0.999) * g * g
+        assert np.abs(m - m1).max() < 1e-16 and np.abs(v - v1).max() < 1e-16
+        assert np.abs(th - (th0 - 0.02 * m1 / (np.sqrt(v1) + 1e-8))).max() < 1e-15
+    z = np.zeros(1)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.qoc_adam_host(p(z), p(z), p(z), p(z), C.c_size_t(0), 0.1, 0.9, 0.999, 1e-8, 4) == 0 and z[0] == 0.0
+    assert lib.qoc_adam_host(None, p(z), p(z), p(z), C.c_size_t(1), 0.1, 0.9, 0.999, 1e-8, 1) == -1      # QOC_EINVAL
