@@ -70,6 +70,18 @@ struct MT {
 #ifndef QOC_CMUL_3M
 #define QOC_CMUL_3M 1
 #endif
+#ifndef QOC_KUNROLL
+#define QOC_KUNROLL 1            // k-steps unrolled in the GEMM loops: C2 expm 5.30 / 5.36 / 5.37 / 5.52 ms at 1 / 2 / 4 / 8
+#endif
+#if QOC_KUNROLL == 2
+#define QOC_PRAGMA_KUNROLL _Pragma("unroll 2")
+#elif QOC_KUNROLL == 4
+#define QOC_PRAGMA_KUNROLL _Pragma("unroll 4")
+#elif QOC_KUNROLL == 8
+#define QOC_PRAGMA_KUNROLL _Pragma("unroll 8")
+#else
+#define QOC_PRAGMA_KUNROLL _Pragma("unroll 1")
+#endif
 
 template <int NP, int RB, int CB>
 DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, double (&cr)[RB][CB][2],
@@ -96,7 +108,7 @@ DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
 #if QOC_CMUL_3M
   // operand sums right where the fragments are loaded: a hand-pipelined variant (sums one k-step ahead) measured
   // 2.5 % slower in the isolated loop (tools/gemm_loop_probe.cu) and in the kernel, and needs more registers
-#pragma unroll 2
+QOC_PRAGMA_KUNROLL
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k = 4 * ks + q;
     cplx a[RB], b[CB];
@@ -125,7 +137,7 @@ DEVINL void mma_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
       for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], sa[i], sb[j]);
   }
 #else
-#pragma unroll 2
+QOC_PRAGMA_KUNROLL
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k = 4 * ks + q;
     cplx a[RB], b[CB];
@@ -224,7 +236,7 @@ DEVINL void tri_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
 #pragma unroll
   for (int b = 0; b < H_::NB; ++b) cr[b][0] = cr[b][1] = ci[b][0] = ci[b][1] = 0.0;
 #if QOC_CMUL_3M
-#pragma unroll 2
+QOC_PRAGMA_KUNROLL
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k = 4 * ks + q;
     const cplx a0 = A[ra * NP + (k ^ ma)], a1 = A[rb * NP + (k ^ mb)];
@@ -251,7 +263,7 @@ DEVINL void tri_gemm(const cplx* __restrict__ A, const cplx* __restrict__ B, dou
     for (int j = 0; j < H_::CB_; ++j) dmma(ci[H_::CA + j][0], ci[H_::CA + j][1], s1, sb[H_::RB_ - H_::RA + j]);
   }
 #else
-#pragma unroll 2
+QOC_PRAGMA_KUNROLL
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k = 4 * ks + q;
     const cplx a0 = A[ra * NP + (k ^ ma)], a1 = A[rb * NP + (k ^ mb)];
@@ -850,7 +862,7 @@ DEVINL void mma_gemm_ah(const cplx* __restrict__ A, const cplx* __restrict__ B, 
     for (int j = 0; j < CB; ++j) t2[i][j][0] = t2[i][j][1] = 0.0;
 #endif
   const int ac = 8 * rb0 + g, bc = 8 * cb0 + g;
-#pragma unroll 2
+QOC_PRAGMA_KUNROLL
   for (int ks = 0; ks < ksteps; ++ks) {
     const int k = 4 * ks + q;
     const int km = sw_mask(k);
