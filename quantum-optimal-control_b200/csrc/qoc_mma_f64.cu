@@ -393,7 +393,9 @@ __host__ __device__ inline size_t expm_item_bytes(int mat, int K) {
   return (size_t)3 * mat * sizeof(cplx) + (((size_t)EXPM_WB * (K + 1) * sizeof(double) + 15) & ~(size_t)15);
 }
 
-template <int NP, int RB, int CB>
+// HERM selects the Hermitian-structure Taylor evaluation at compile time (the host checks the generators), so that
+// each instantiation carries one path only: smaller code for the 8 warps of an SM that sit in different phases of it.
+template <int NP, int RB, int CB, bool HERM>
 __global__ void __launch_bounds__(MT<NP, RB, CB>::WARPS == 1 ? 128 : MT<NP, RB, CB>::THREADS)
 k_expm_mma(QocParams p) {
   typedef MT<NP, RB, CB> T_;
@@ -469,9 +471,7 @@ k_expm_mma(QocParams p) {
     // B_i = c_{2i} I + c_{2i+1} H, c_j = 1/j!  -> 1 + floor(p/2) - [p even] products instead of p-1.
     double sr[RB][CB][2], si[RB][CB][2];
     // Hermitian Hamiltonians (all generators anti-Hermitian): triangle-only products, see herm_taylor
-    constexpr bool HERM_OK = (NP == 32 && RB == 2 && CB == 4) || (NP == 16 && RB == 2 && CB == 2);
-    const bool use_herm = HERM_OK && p.herm && p.p >= 2;
-    if (HERM_OK && use_herm) {
+    if constexpr (HERM) {
       if (NP == 32) {
         if (warp == 0) herm_taylor<NP, 0, WARPS>(p, Hs, buf1, buf2, n, ksteps, lane);
         else herm_taylor<NP, (NP == 32 ? 1 : 0), WARPS>(p, Hs, buf1, buf2, n, ksteps, lane);
@@ -805,24 +805,35 @@ cudaError_t launch_segprod(const QocParams& p, int L, int S, cplx* seg_out, cuda
   return cudaGetLastError();
 }
 
-template <int NP, int RB, int CB>
-cudaError_t launch_expm(const QocParams& p, int sm_count, cudaStream_t st) {
+template <int NP, int RB, int CB, bool HERM>
+cudaError_t launch_expm_h(const QocParams& p, int sm_count, cudaStream_t st) {
   typedef MT<NP, RB, CB> T_;
   const int ipc = T_::WARPS == 1 ? 4 : 1;
   const int threads = T_::WARPS == 1 ? 128 : T_::THREADS;
   const size_t smem = expm_item_bytes(T_::MAT, p.K) * ipc;
-  cudaError_t e = cudaFuncSetAttribute(k_expm_mma<NP, RB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_expm_mma<NP, RB, CB, HERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expm_mma<NP, RB, CB>, threads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expm_mma<NP, RB, CB, HERM>, threads, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) occ = 1;
   const long long items = (long long)p.B * p.T;
   long long grid = (long long)sm_count * occ;
   const long long need = (items + ipc - 1) / ipc;
   if (grid > need) grid = need;
-  k_expm_mma<NP, RB, CB><<<(unsigned)grid, threads, smem, st>>>(p);
+  k_expm_mma<NP, RB, CB, HERM><<<(unsigned)grid, threads, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+// Hermitian Hamiltonians (all generators anti-Hermitian, checked on the host) take the triangle-only Taylor
+// evaluation where the tile shape supports it (NP = 16, 32)
+template <int NP, int RB, int CB>
+cudaError_t launch_expm(const QocParams& p, int sm_count, cudaStream_t st) {
+  constexpr bool HERM_OK = (NP == 32 && RB == 2 && CB == 4) || (NP == 16 && RB == 2 && CB == 2);
+  if constexpr (HERM_OK) {
+    if (p.herm && p.p >= 2) return launch_expm_h<NP, RB, CB, true>(p, sm_count, st);
+  }
+  return launch_expm_h<NP, RB, CB, false>(p, sm_count, st);
 }
 
 template <int NP, int RB, int CB, int NPB, int NXB, bool PF32 = false>
