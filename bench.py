@@ -20,8 +20,10 @@ import os
 # The e2e leg alternates a ~7 ms GPU wait with a short multi-threaded host update (qoc_adam_host): with libgomp's
 # default passive wait policy the worker threads are asleep by then and waking them costs more than the update itself
 # (tools/e2e_breakdown.py: 7.94 ms per C2 step passive / 4 threads vs 7.39 ms active / 16 threads).  Must be set before
-# the OpenMP runtime is loaded; an explicit setting in the environment wins.
-os.environ.setdefault("OMP_WAIT_POLICY", "ACTIVE")
+# the OpenMP runtime is loaded; an explicit setting in the environment wins.  Single-process runs only: with one rank
+# per GPU the ranks share the host's cores and spinning workers would fight each other (measured passive there).
+if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ.setdefault("OMP_WAIT_POLICY", "ACTIVE")
 import subprocess
 import sys
 import threading
@@ -259,7 +261,7 @@ def run_ours(args):
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))      # host Adam: share the cores between ranks
     hbase = eng.host_buffers()['base']                      # pinned host weights, updated in place by the host Adam
     hbase[...] = np.asarray(sp.ops_weight_base, dtype=np.float64)
-    hadam = HostAdam(hbase.shape, threads=max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
+    hadam = HostAdam(hbase.shape, threads=max(1, min(16 if world == 1 else 4, (os.cpu_count() or 1) // max(world, 1))))
     for _ in range(max(3, min(args.warmup, 5))):
         o = eng.value_and_grad_host(hbase, copy=False)
         hadam.step(hbase, o['grad'], lr)
