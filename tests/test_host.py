@@ -230,3 +230,20 @@ def test_qoc_adam_host_c_entry_point():
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     assert lib.qoc_adam_host(p(z), p(z), p(z), p(z), C.c_size_t(0), 0.1, 0.9, 0.999, 1e-8, 4) == 0 and z[0] == 0.0
     assert lib.qoc_adam_host(None, p(z), p(z), p(z), C.c_size_t(1), 0.1, 0.9, 0.999, 1e-8, 1) == -1      # QOC_EINVAL
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle in reference-cost mode; the only place outside tests/ and smoke()
+    that executes oracle/) prints ONE JSON line with the keys the driver reads; shortened time grid so it takes seconds."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--steps-T", "20"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "instance-iterations/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "T=20" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
