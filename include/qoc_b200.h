@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define QOC_ABI_VERSION 1
+#define QOC_ABI_VERSION 2
 
 enum {
   QOC_OK = 0,
@@ -59,7 +59,10 @@ enum {
 /* arithmetic of the propagator (expm + chain) stage */
 enum {
   QOC_F64 = 0,          /* IEEE double on the FP64 pipe (parity / config C2) */
-  QOC_TF32X3 = 1        /* fp32-class: tcgen05 kind::tf32 with 3-way operand split, fp32 accumulate in TMEM */
+  QOC_TF32X3 = 1,       /* fp32-class, n <= 32: tcgen05 kind::tf32 with 3-way operand split, fp32 accumulate in TMEM */
+  QOC_F16X2 = 2         /* fp32-class, n <= 256, m <= 8: tcgen05 kind::f16 on TMA-fed tiles, every real number held as a pair
+                         * of fp16 halves (22+ bits, the size of the reference's float32), three MMAs per real product,
+                         * fp32 accumulate in TMEM; propagators cached as split fp16 planes; states / costates stay fp64 */
 };
 
 /* qoc_dims_t.flags */
@@ -153,7 +156,9 @@ int qoc_evolve_host(qoc_handle_t h, const double* base_host, double* U_final_hos
                     double* loss_host, double* unitary_scale_host, void* stream);
 
 /* Read-only views into the workspace after a value_and_grad / evolve call (device pointers):
- * propagators P[B][T][n][n] (complex double for QOC_F64, complex float for QOC_TF32X3). */
+ * propagators P[B][T][n][n] (complex double for QOC_F64, complex float tiles for QOC_TF32X3; for QOC_F16X2
+ * elem_bytes = 2 and the layout is [B][T][4][n][ld] fp16 planes (Re h0, Re h1, Im h0, Im h1), ld = n rounded up
+ * to 16, value = (h0 + h1) / 8192). */
 int qoc_debug_propagators(qoc_handle_t h, void** P_dev, int* elem_bytes);
 
 /* Instances processed per pass.  When the workspace for all B instances would exceed the memory budget

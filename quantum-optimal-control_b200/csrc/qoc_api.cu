@@ -15,14 +15,24 @@ static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 static int pick_np(int n) { return n <= 64 ? (n + 7) / 8 * 8 : -1; }
 
-struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, seg, scratch, total; };
+struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, seg, scratch, tc_seg, tc_scr, tc_const, total; };
+
+#define QOC_TC_SEG_LEN 16   // propagators per segment product of the QOC_F16X2 U_final branch
+
+static int tc_grid_for(const qoc_dims_t& d, int sm_count) {
+  TcGeom g;
+  if (!tc_geometry(d.n, &g)) return 0;
+  return sm_count * g.ctas_per_sm;
+}
 
 static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
   // Bc = instances processed per pass (batch chunk); P / psi / lam / gctrl / ot / scratch are reused by every pass
   WsLayout L;
   const size_t nn = (size_t)d.n * d.n, mn = (size_t)d.m * d.n;
   // propagators: fp64 interleaved [n][n] complex, or (QOC_TF32X3) fp32 planar padded [2][32][32]
-  const size_t p_item = d.dtype == QOC_F64 ? nn * sizeof(cplx) : (size_t)2 * 32 * 32 * sizeof(float);
+  const bool tc = d.dtype == QOC_F16X2;
+  const size_t tc_mat = tc ? (size_t)4 * d.n * tc_ld(d.n) * sizeof(__half) : 0;      // one split-plane matrix
+  const size_t p_item = d.dtype == QOC_F64 ? nn * sizeof(cplx) : tc ? tc_mat : (size_t)2 * 32 * 32 * sizeof(float);
   size_t off = 0;
   L.P = off; off += align_up((size_t)Bc * d.T * p_item);
   L.psi = off; off += align_up((size_t)Bc * (d.T + 1) * mn * sizeof(cplx));
@@ -35,10 +45,17 @@ static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
   L.st_grad = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_out = off; off += align_up((size_t)d.B * 4 * sizeof(double));
   L.seg = off;                                   // segment products of the re-associated U_final chain (n <= 64, fp64)
-  if (d.n <= 64)
+  if (d.n <= 64 && !tc)
     off += align_up((size_t)Bc * ((d.T + QOC_SEG_LEN - 1) / QOC_SEG_LEN) * nn * sizeof(cplx));
   L.scratch = off;
-  if (d.n > 64) off += align_up(qoc_large_scratch_elems(d.n, Bc, sm_count) * sizeof(cplx));
+  if (d.n > 64 && !tc) off += align_up(qoc_large_scratch_elems(d.n, Bc, sm_count) * sizeof(cplx));
+  L.tc_seg = L.tc_scr = L.tc_const = off;
+  if (tc) {
+    off = align_up(off, 1024);
+    L.tc_seg = off; off += align_up((size_t)Bc * ((d.T + QOC_TC_SEG_LEN - 1) / QOC_TC_SEG_LEN) * tc_mat, 1024);
+    L.tc_scr = off; off += align_up((size_t)tc_grid_for(d, sm_count) * TC_NSLOT * tc_mat, 1024);
+    L.tc_const = off; off += align_up(2 * tc_mat, 1024);
+  }
   L.total = off;
   return L;
 }
@@ -54,7 +71,7 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   if (d.n < 1 || d.K < 0 || d.K > 31 || d.T < 1 || d.m < 1 || d.B < 1 || d.exp_terms < 1 || d.exp_terms > 31 || ((d.flags & QOC_FLAG_STATE_TRANSFER) && d.exp_terms < 2) || d.scaling < 0 ||
       d.scaling > 60)
     return QOC_EINVAL;
-  if (d.dtype != QOC_F64 && d.dtype != QOC_TF32X3) return QOC_EINVAL;
+  if (d.dtype != QOC_F64 && d.dtype != QOC_TF32X3 && d.dtype != QOC_F16X2) return QOC_EINVAL;
   qoc_handle_s* h = new (std::nothrow) qoc_handle_s();
   if (!h) return QOC_ENOMEM;
   h->d = d;
@@ -74,6 +91,9 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
   h->profiling = false; h->ev_recorded = 0;
   for (int i = 0; i <= QOC_NUM_KERNELS; ++i) h->ev[i] = nullptr;
   h->hi = nullptr; h->ev_fork = h->ev_join = nullptr; h->hi_pending = false; h->work = nullptr; h->seg = nullptr;
+  h->tc = d.dtype == QOC_F16X2; h->tc_ready = false;
+  h->tc_seg = h->tc_scr = h->tc_const = nullptr; h->tc_ops = nullptr; h->tc_nops = 0; h->tc_xscale = 0.f;
+  h->A_f = nullptr; h->U0_host = nullptr; h->tc_grid = 0; h->tc_S = 0;
   *out = h;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -102,6 +122,15 @@ int qoc_create(qoc_handle_t* out, const qoc_dims_t* dims) {
       }
     }
   }
+  if (h->tc) {
+    if (d.n > TC_MAX_N || d.K > 31 || (d.flags & QOC_FLAG_STATE_TRANSFER) || !qoc_plane_sweep_supported(d.n, d.m) ||
+        !tc_geometry(d.n, &h->tg)) {
+      h->err = "QOC_F16X2 (tcgen05 / TMA path) supports n <= 256, m <= 8, unitary mode in this build";
+      return QOC_EINVAL;
+    }
+    h->tc_grid = tc_grid_for(d, h->sm_count);
+    h->tc_S = (d.T + QOC_TC_SEG_LEN - 1) / QOC_TC_SEG_LEN;
+  }
   if (d.dtype == QOC_TF32X3 && (d.n > 32 || d.K > 15)) {
     h->err = "QOC_TF32X3 (tcgen05 path) supports n <= 32, K <= 15 in this build";
     return QOC_EINVAL;
@@ -125,6 +154,7 @@ int qoc_destroy(qoc_handle_t h) {
   QOC_CHECK_H(h);
   cudaFree(h->A); cudaFree(h->U0); cudaFree(h->phi); cudaFree(h->V); cudaFree(h->coo_v);
   cudaFree(h->cidx); cudaFree(h->coo_off); cudaFree(h->coo_r); cudaFree(h->coo_c);
+  cudaFree(h->tc_ops); cudaFree(h->A_f); free(h->U0_host);
   cudaFree(h->maxA); cudaFree(h->env); cudaFree(h->fw); cudaFree(h->dressW); cudaFree(h->psid); cudaFree(h->pat_rc); cudaFree(h->pat_coef); cudaFree(h->pat_coef_f); cudaFree(h->err_flag);
   for (int i = 0; i <= QOC_NUM_KERNELS; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->hi) { cudaStreamSynchronize(h->hi); cudaStreamDestroy(h->hi); }
@@ -157,6 +187,8 @@ int qoc_set_workspace(qoc_handle_t h, void* dev_ptr, size_t bytes) {
   h->st_base = (double*)(w + L.st_base); h->st_grad = (double*)(w + L.st_grad); h->st_out = (double*)(w + L.st_out);
   h->seg = (cplx*)(w + L.seg);
   h->scratch = w + L.scratch;
+  h->tc_seg = (__half*)(w + L.tc_seg); h->tc_scr = (__half*)(w + L.tc_scr); h->tc_const = (__half*)(w + L.tc_const);
+  h->tc_ready = false;
   h->ws_set = true;
   return QOC_OK;
 }
@@ -256,6 +288,41 @@ int qoc_set_problem(qoc_handle_t h, const double* A_host, const double* U0_host,
   CUDA_TRY(h, upload(&h->coo_r, rr.data(), rr.size(), st));
   CUDA_TRY(h, upload(&h->coo_c, cc.data(), cc.size(), st));
   CUDA_TRY(h, upload(&h->coo_v, vv.data(), vv.size() / 2, st));
+  if (h->tc) {
+    if (!h->herm) { h->err = "QOC_F16X2 needs Hermitian H0 / Hops (anti-Hermitian generators)"; return QOC_EINVAL; }
+    // entrywise bound |X| <= (|A_0| + sum_k maxA_k |A_k|) / 2^s and a bound of its 2-norm pick the power-of-two scales
+    std::vector<double> bnd(nn, 0.0);
+    for (int k = 0; k <= d.K; ++k) {
+      const double w = k == 0 ? 1.0 : fabs(maxA_host[k - 1]);
+      for (size_t i = 0; i < nn; ++i) bnd[i] += w * hypot(A_host[((size_t)k * nn + i) * 2], A_host[((size_t)k * nn + i) * 2 + 1]);
+    }
+    double xmax = 0.0, fro = 0.0, n1 = 0.0, ninf = 0.0;
+    std::vector<double> colsum(d.n, 0.0);
+    for (int r = 0; r < d.n; ++r) {
+      double rs = 0.0;
+      for (int c = 0; c < d.n; ++c) { const double v = bnd[(size_t)r * d.n + c]; xmax = v > xmax ? v : xmax; fro += v * v; rs += v; colsum[c] += v; }
+      ninf = rs > ninf ? rs : ninf;
+    }
+    for (int c = 0; c < d.n; ++c) n1 = colsum[c] > n1 ? colsum[c] : n1;
+    const double inv2s = ldexp(1.0, -d.scaling);
+    double theta = sqrt(n1 * ninf);
+    if (sqrt(fro) < theta) theta = sqrt(fro);
+    int eX, eY;
+    tc_pick_scales(xmax * inv2s, theta * inv2s, &eX, &eY);
+    std::vector<TcExpmOp> ops;
+    tc_build_expm_ops(d.exp_terms, d.scaling, eX, eY, ops);
+    h->tc_nops = (int)ops.size();
+    h->tc_xscale = (float)ldexp(1.0, eX - d.scaling);
+    CUDA_TRY(h, upload(&h->tc_ops, ops.data(), ops.size(), st));
+    std::vector<float> af((size_t)(d.K + 1) * nn * 2);
+    for (size_t i = 0; i < af.size(); ++i) af[i] = (float)A_host[i];
+    CUDA_TRY(h, upload(&h->A_f, af.data(), af.size() / 2, st));
+    free(h->U0_host);
+    h->U0_host = (double*)malloc(nn * 2 * sizeof(double));
+    if (!h->U0_host) return QOC_ENOMEM;
+    std::memcpy(h->U0_host, U0_host, nn * 2 * sizeof(double));
+    h->tc_ready = false;
+  }
   CUDA_TRY(h, cudaStreamSynchronize(st));       // host vectors above go out of scope
   h->has_cidx = concerned_idx ? 1 : 0;
   h->dt = dt;
@@ -381,6 +448,65 @@ static int launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   return QOC_OK;
 }
 
+// QOC_F16X2: constant plane sets (U0, I) and the TMA descriptors need both the problem and the workspace
+static int tc_prepare(qoc_handle_t h, cudaStream_t st) {
+  if (h->tc_ready) return QOC_OK;
+  const qoc_dims_t& d = h->d;
+  const TcGeom& g = h->tg;
+  std::vector<__half> hbuf(2 * g.mat_halfs);
+  std::vector<double> I((size_t)d.n * d.n * 2, 0.0);
+  for (int i = 0; i < d.n; ++i) I[((size_t)i * d.n + i) * 2] = 1.0;
+  tc_pack_host(h->U0_host, d.n, g.ld, TC_EU, hbuf.data());
+  tc_pack_host(I.data(), d.n, g.ld, TC_EU, hbuf.data() + g.mat_halfs);
+  CUDA_TRY(h, cudaMemcpyAsync(h->tc_const, hbuf.data(), hbuf.size() * sizeof(__half), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  const void* base[TC_NCLS] = {h->tc_scr, h->P, h->tc_seg, h->tc_const};
+  const unsigned long long cnt[TC_NCLS] = {(unsigned long long)h->tc_grid * TC_NSLOT, (unsigned long long)h->Bc * d.T,
+                                           (unsigned long long)h->Bc * h->tc_S, 2ull};
+  for (int c = 0; c < TC_NCLS; ++c) {
+    const char* e = tc_make_map(&h->tmaps.a[c], base[c], d.n, g.ld, cnt[c], false);
+    if (!e) e = tc_make_map(&h->tmaps.b[c], base[c], d.n, g.ld, cnt[c], true);
+    if (e) { h->err = e; return QOC_ECUDA; }
+  }
+  h->tc_ready = true;
+  return QOC_OK;
+}
+
+static void tc_base_params(qoc_handle_t h, TcParams& q) {
+  std::memset(&q, 0, sizeof(q));
+  q.base[TC_CLS_SCR] = h->tc_scr; q.base[TC_CLS_P] = (__half*)h->P; q.base[TC_CLS_SEG] = h->tc_seg; q.base[TC_CLS_CONST] = h->tc_const;
+  q.err_flag = h->err_flag;
+}
+
+static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
+  TcParams q;
+  tc_base_params(h, q);
+  q.prog = TC_PROG_EXPM; q.items = (long long)p.B * p.T;
+  q.nops = h->tc_nops; q.ops = h->tc_ops; q.K = p.K; q.T = p.T; q.ctrl = p.base; q.maxA = p.maxA; q.A_f = h->A_f; q.xscale = h->tc_xscale;
+  ++h->launches;
+  CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(q.items < h->tc_grid ? q.items : h->tc_grid), st));
+  return QOC_OK;
+}
+
+// U_final / unitary_scale: segment products (16 propagators each) + the chain over the segments, all on tcgen05
+static int tc_launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
+  TcParams q;
+  tc_base_params(h, q);
+  const int L = QOC_TC_SEG_LEN, S = (p.T + L - 1) / L;
+  if (S >= 2) {
+    q.prog = TC_PROG_SEG; q.items = (long long)p.B * S; q.T = p.T; q.L = L; q.S = S;
+    ++h->launches;
+    CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(q.items < h->tc_grid ? q.items : h->tc_grid), st));
+  }
+  tc_base_params(h, q);
+  q.prog = TC_PROG_CHAIN; q.items = p.B;
+  q.chain_cls = S >= 2 ? TC_CLS_SEG : TC_CLS_P; q.chain_len = S >= 2 ? S : p.T;
+  q.Ufin = p.Ufin; q.scal = p.scal;
+  ++h->launches;
+  CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(q.items < h->tc_grid ? q.items : h->tc_grid), st));
+  return QOC_OK;
+}
+
 // Forward pass.  On return h->work is the stream the caller must use for everything that consumes psi
 // (fwd_reduce has run on it); join_hi() brings the caller's stream back in.
 static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
@@ -389,6 +515,28 @@ static int run_forward(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   if ((rc = join_hi(h, st))) return rc;
   h->work = st;
   if ((rc = prof_mark(h, 0, st))) return rc;
+  if (h->tc) {
+    // propagators on tcgen05 (TMA-fed fp16-pair tiles); then the two-branch tail of the few-state problems: the state
+    // sweep over the split-plane propagators on the high-priority stream, the U_final products on tcgen05 beside it
+    if ((rc = tc_prepare(h, st))) return rc;
+    if ((rc = tc_launch_expm(h, p, st))) return rc;
+    if ((rc = prof_mark(h, 1, st))) return rc;
+    static const int xmode = getenv("QOC_B200_XCHAIN") ? atoi(getenv("QOC_B200_XCHAIN")) : 2;
+    if (xmode == 2) {
+      CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->hi, h->ev_fork, 0));
+      h->work = h->hi;
+      h->hi_pending = true;
+    }
+    CUDA_TRY(h, qoc_launch_plane_sweep(p, h->P, 0, h->work, &h->launches));
+    if (xmode != 0 && (rc = tc_launch_xchain(h, p, st))) return rc;
+    cudaStream_t ws = h->work;
+    if ((rc = prof_mark(h, 2, ws))) return rc;
+    if (p.dressW) CUDA_TRY(h, qoc_launch_dress(p, 0, ws, &h->launches));
+    CUDA_TRY(h, qoc_launch_fwd_reduce(p, ws, &h->launches));
+    if ((rc = prof_mark(h, 3, ws))) return rc;
+    return QOC_OK;
+  }
   const bool large = h->d.n > 64;                   // matrices do not fit in shared memory: tiled global-operand path
   if (h->d.dtype == QOC_TF32X3) CUDA_TRY(h, qoc_launch_expm_tc32(p, h->sm_count, h->err_flag, st, &h->launches));
   else if (large) CUDA_TRY(h, qoc_launch_expm_large(p, h->sm_count, h->scratch, st, &h->launches));
@@ -434,7 +582,8 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
     // dense-m problems (m >= NP/2, dense controls) take the DMMA costate / gradient kernels
     const bool dense_m = h->d.n <= 64 && h->d.dtype == QOC_F64 && 2 * h->d.m >= h->NP && h->d.m <= h->NP;
     const bool dense_A = (double)h->nnz >= 0.25 * (double)h->d.K * h->d.n * h->d.n;
-    if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, ws, &h->launches));
+    if (h->tc) CUDA_TRY(h, qoc_launch_plane_sweep(p, h->P, 1, ws, &h->launches));
+    else if (h->d.n > 64) CUDA_TRY(h, qoc_launch_costate_large(p, ws, &h->launches));
     else if (dense_m) CUDA_TRY(h, qoc_launch_costate_mma(p, h->NP, ws, &h->launches));
     else if (use_vec_sweeps(h, p)) CUDA_TRY(h, qoc_launch_vec_sweep(p, 1, h->d.dtype != QOC_F64, ws, &h->launches));
     else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, ws, &h->launches));
@@ -551,7 +700,7 @@ int qoc_debug_propagators(qoc_handle_t h, void** P_dev, int* elem_bytes) {
   QOC_CHECK_H(h);
   if (!h->ws_set) return QOC_ESTATE;
   if (P_dev) *P_dev = h->P;
-  if (elem_bytes) *elem_bytes = h->d.dtype == QOC_F64 ? (int)sizeof(cplx) : (int)sizeof(float2);
+  if (elem_bytes) *elem_bytes = h->d.dtype == QOC_F64 ? (int)sizeof(cplx) : h->tc ? (int)sizeof(__half) : (int)sizeof(float2);
   return QOC_OK;
 }
 
@@ -564,7 +713,7 @@ int qoc_poll_error(qoc_handle_t h, void* stream) {
   int flag = 0;
   CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
   CUDA_TRY(h, cudaMemcpy(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) { h->err = "tcgen05 pipeline timed out waiting for an MMA completion barrier"; return QOC_ECUDA; }
+  if (flag) { h->err = "tcgen05 pipeline timed out waiting for a TMA / MMA completion barrier"; return QOC_ECUDA; }
   return QOC_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include "qoc_b200.h"
+#include "qoc_tc_f16.cuh"
 
 typedef double2 cplx;
 
@@ -82,6 +83,14 @@ struct qoc_handle_s {
   bool hi_pending;
   cudaStream_t work;                      // where the current pass's sweep / gradient kernels go (hi or the caller's stream)
   cplx* seg;                              // [Bc][ceil(T/QOC_SEG_LEN)][n][n] segment products
+  // QOC_F16X2: tcgen05 / TMA program engine (qoc_tc_f16.cu)
+  bool tc, tc_ready;
+  TcGeom tg; TcMaps tmaps;
+  __half *tc_seg, *tc_scr, *tc_const;     // plane-set arrays inside the workspace (P is h->P)
+  TcExpmOp* tc_ops; int tc_nops; float tc_xscale;
+  float2* A_f;                            // dense fp32 copy of A_0..A_K for the generator assembly
+  double* U0_host;                        // kept for the constant plane sets
+  int tc_grid, tc_S;
   cudaEvent_t ev[QOC_NUM_KERNELS + 1];
 };
 
@@ -104,3 +113,5 @@ cudaError_t qoc_launch_fwd_reduce(const QocParams& p, cudaStream_t st, int64_t* 
 cudaError_t qoc_launch_costate(const QocParams& p, int p_is_f32, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_grad(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_finalize(const QocParams& p, cudaStream_t st, int64_t* launches);
+bool qoc_plane_sweep_supported(int n, int m);
+cudaError_t qoc_launch_plane_sweep(const QocParams& p, const void* planes, int reverse, cudaStream_t st, int64_t* launches);

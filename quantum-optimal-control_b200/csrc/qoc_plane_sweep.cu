@@ -1,0 +1,322 @@
+// State / costate sweeps over split-plane (QOC_F16X2) propagators, few concerned states (m <= 8), n <= 256.
+//
+//   k_plane_sweep<false>: psi_j(t+1) = P_t psi_j(t)                          (init_tf_inter_vectors, core/tensorflow_state.py:229-242)
+//   k_plane_sweep<true> : lambda_j(t) = P_t^dagger lambda_j(t+1) + source_j(t)   (TF autodiff through :214-220)
+//
+// One CTA per instance walks the T steps; a step reads the 8 n ld bytes of P_t exactly once from HBM, in
+// 16-row chunks (4 planes x 16 rows, one cp.async.bulk per plane) through an NST-deep shared-memory ring with
+// an mbarrier per stage.  2^13 P = h0 + h1 is exact in fp32 and widened to double; the states stay fp64.
+//   forward: warp = row of the chunk, lane = pair of k (4-byte loads of P, 16-byte loads of the even-k / odd-k halves
+//            of the state vectors: all conflict-free); the 2 m partial sums meet in a shuffle reduce-scatter;
+//   reverse: thread = (column pair, state pair) keeps its four complex sums in registers over all chunks of the
+//            step, every shared-memory read of P is a conflict-free 4-byte load, lambda is a broadcast.
+#include "qoc_internal.cuh"
+#include "qoc_tc_f16.cuh"
+#include <math.h>
+
+#define DEVINL __device__ __forceinline__
+
+namespace {
+
+constexpr int R = 16;          // rows per chunk (one per warp in the forward sweep)
+constexpr int NTH = 512;
+
+DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVINL void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+DEVINL void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+DEVINL cplx cmul(const cplx a, const cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+[[maybe_unused]] DEVINL void widen8(const uint4 h0, const uint4 h1, double (&v)[8]) {
+  const uint32_t a[4] = {h0.x, h0.y, h0.z, h0.w}, b[4] = {h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a[i]));
+    const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&b[i]));
+    v[2 * i] = (double)(fa.x + fb.x); v[2 * i + 1] = (double)(fa.y + fb.y);
+  }
+}
+DEVINL double2 widen2(uint32_t h0, uint32_t h1) {
+  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+  const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+  return make_double2((double)(fa.x + fb.x), (double)(fa.y + fb.y));
+}
+
+struct PlaneSweepShape { int nst; size_t stage_halfs, smem; };
+
+PlaneSweepShape plane_sweep_shape(int n, int m) {
+  PlaneSweepShape s;
+  const int ld = tc_ld(n);
+  s.stage_halfs = (size_t)4 * R * ld;
+  const size_t vec = (size_t)2 * 8 * ld * sizeof(cplx);          // [2][8][2][ld/2]
+  const size_t fixed = vec + 64 + 128;
+  int nst = (int)((220 * 1024 - fixed) / (s.stage_halfs * sizeof(__half)));
+  if (nst > 8) nst = 8;
+  s.nst = nst;
+  s.smem = fixed + (size_t)(nst > 0 ? nst : 0) * s.stage_halfs * sizeof(__half);
+  (void)m;
+  return s;
+}
+
+// butterfly reduce-scatter of 2*MS doubles over the 32 lanes: afterwards lane L (L even) holds the warp sum of element
+// idx(L) = L >> (5 - log2(2 MS)) ... expressed below by halving the live set at every step
+template <int NV>
+DEVINL double reduce_scatter(double (&a)[NV], int lane, int& idx) {
+  int base = 0;
+#pragma unroll
+  for (int cnt = NV, off = 16; cnt > 1; cnt >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+    const int h = cnt >> 1;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? a[i] : a[i + h];
+      const double keep = up ? a[i + h] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    base = 2 * base + (up ? 1 : 0);
+  }
+  // remaining lane bits hold replicas of partial sums: finish with plain butterflies
+  double v = a[0];
+  int off = 16;
+#pragma unroll
+  for (int cnt = NV; cnt > 1; cnt >>= 1) off >>= 1;
+  for (; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  idx = base;          // element index in "bit-reversed halving" order: see caller
+  return v;
+}
+
+template <bool REV, int MS>
+__global__ void __launch_bounds__(NTH) k_plane_sweep(QocParams p, const __half* __restrict__ Pp, int NST) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = p.n, m = p.m, T = p.T, mn = m * n;
+  const int ld = tc_ld(n), lh = ld >> 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const size_t stage_halfs = (size_t)4 * R * ld;
+  __half* ring = reinterpret_cast<__half*>(smem_raw);                                    // [NST][4][R][ld]
+  cplx* vecs = reinterpret_cast<cplx*>(smem_raw + (size_t)NST * stage_halfs * sizeof(__half));   // [2][8][2][ld/2]: even / odd k split
+  uint64_t* full = reinterpret_cast<uint64_t*>(vecs + (size_t)2 * 8 * ld);               // [NST]
+  const size_t plane = (size_t)n * ld, mat = 4 * plane;
+  const __half* Pb = Pp + (size_t)b * T * mat;
+  cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
+  cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn;
+  const int NC = (n + R - 1) / R;
+  const int nsteps = REV ? T - 1 : T;
+  const long long nchunks = (long long)nsteps * NC;
+  const double pscale = 1.0 / (double)(1 << TC_EU);
+  auto vidx = [&](int j, int k) { return (size_t)(2 * j + (k & 1)) * lh + (k >> 1); };
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto prefetch = [&](long long g) {                       // chunk g (sweep order) -> stage g % NST; one thread, 4 bulk copies
+    if (g < nchunks) {
+      const int step = (int)(g / NC), c = (int)(g - (long long)step * NC);
+      const int t = REV ? T - 1 - step : step;
+      const int rows = min(R, n - c * R);
+      uint64_t* bar = &full[g % NST];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t bytes = (uint32_t)(rows * ld * sizeof(__half));
+      mbar_expect_tx(bar, 4 * bytes);
+      __half* dst = ring + (size_t)(g % NST) * stage_halfs;
+      const __half* src = Pb + (size_t)t * mat + (size_t)c * R * ld;
+#pragma unroll
+      for (int pl = 0; pl < 4; ++pl) bulk_g2s(dst + (size_t)pl * R * ld, src + (size_t)pl * plane, bytes, bar);
+    }
+  };
+  if (tid == 0)
+    for (int i = 0; i < NST - 1; ++i) prefetch(i);
+
+  const bool forb = REV && p.reg.has_forbidden && p.fw != nullptr;
+  const bool spd = REV && p.reg.has_speed_up != 0;
+  const double* sc = p.scal + (size_t)b * 8;
+  const double spdfac = REV ? sc[4] : 0.0;
+  auto source = [&](int t, int j, int r) -> cplx {         // regulariser sources (core/regularization_functions.py:71-95)
+    cplx s = make_double2(0.0, 0.0);
+    if (forb && p.dressW) {
+      s = p.psid[((size_t)b * (T + 1) + t) * mn + (size_t)j * n + r];
+    } else if (forb) {
+      const cplx x = psi_b[(size_t)t * mn + (size_t)j * n + r];
+      const double c = p.fw[r] / (double)T * 2.0 * (x.x * x.x + x.y * x.y);
+      s.x = c * x.x; s.y = c * x.y;
+    }
+    if (spd) {
+      const cplx q = cmul(p.ot[(size_t)b * (T + 1) + t], p.phi[(size_t)j * n + r]);
+      s.x += spdfac * q.x; s.y += spdfac * q.y;
+    }
+    return s;
+  };
+
+  // initial vectors, zero-padded
+  for (int e = tid; e < 2 * 8 * ld; e += NTH) vecs[e] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int e = tid; e < m * n; e += NTH) {
+    const int j = e / n, r = e - j * n;
+    cplx v = make_double2(0.0, 0.0);
+    if (REV) {                                             // lambda(T) = -(2/m^2) o phi + source(T)
+      const double f = -2.0 / ((double)m * (double)m);
+      v = cmul(make_double2(sc[0] * f, sc[1] * f), p.phi[(size_t)j * n + r]);
+      const cplx s = source(T, j, r);
+      v.x += s.x; v.y += s.y;
+      lam_b[(size_t)T * mn + (size_t)j * n + r] = v;
+    } else {                                               // psi(0) = V is stored as is (:233-234); the chain starts from U0 V
+      for (int c = 0; c < n; ++c) {
+        const cplx u = p.U0[(size_t)r * n + c], a = p.V[(size_t)j * n + c];
+        v.x += u.x * a.x - u.y * a.y; v.y += u.x * a.y + u.y * a.x;
+      }
+      psi_b[(size_t)j * n + r] = p.V[(size_t)j * n + r];
+    }
+    vecs[vidx(j, r)] = v;
+  }
+
+  int cur = 0;
+  long long g = 0;
+  if (!REV) {
+    // warp = row (rows warp, warp + 16 of the chunk), lane = pair of k; every shared-memory access is conflict-free
+    // (P: consecutive 4-byte words; v: consecutive 16-byte elements of the even-k / odd-k halves)
+    for (int step = 0; step < nsteps; ++step) {
+      const cplx* vc = vecs + (size_t)cur * 8 * ld;
+      cplx* vn = vecs + (size_t)(cur ^ 1) * 8 * ld;
+      for (int c = 0; c < NC; ++c, ++g) {
+        __syncthreads();                                   // previous chunk's stage is free; for c = 0: v(cur) complete
+        if (tid == 0) prefetch(g + NST - 1);
+        while (!mbar_try_wait(&full[g % NST], (uint32_t)(g / NST) & 1u)) {}
+        const uint32_t* St = reinterpret_cast<const uint32_t*>(ring + (size_t)(g % NST) * stage_halfs);
+        const size_t pw = (size_t)R * lh;                  // plane stride in 32-bit words
+#pragma unroll 1
+        for (int rr = warp; rr < R; rr += 16) {
+          const int row = c * R + rr;
+          if (row >= n) break;                             // warp-uniform
+          double a[2 * MS];
+#pragma unroll
+          for (int i = 0; i < 2 * MS; ++i) a[i] = 0.0;
+          const uint32_t* wr = St + (size_t)rr * lh;
+          for (int w = lane; w < lh; w += 32) {
+            const double2 er = widen2(wr[w], wr[pw + w]);  // Re of k = 2w, 2w+1
+            const double2 ei = widen2(wr[2 * pw + w], wr[3 * pw + w]);
+#pragma unroll
+            for (int j = 0; j < MS; ++j) {
+              const cplx x = vc[(size_t)(2 * j) * lh + w], y = vc[(size_t)(2 * j + 1) * lh + w];
+              a[2 * j] = fma(er.x, x.x, a[2 * j]); a[2 * j] = fma(-ei.x, x.y, a[2 * j]);
+              a[2 * j] = fma(er.y, y.x, a[2 * j]); a[2 * j] = fma(-ei.y, y.y, a[2 * j]);
+              a[2 * j + 1] = fma(er.x, x.y, a[2 * j + 1]); a[2 * j + 1] = fma(ei.x, x.x, a[2 * j + 1]);
+              a[2 * j + 1] = fma(er.y, y.y, a[2 * j + 1]); a[2 * j + 1] = fma(ei.y, y.x, a[2 * j + 1]);
+            }
+          }
+          // reduce-scatter: at every step the lower / upper half of the live elements stays with (lane & off) == 0 / != 0,
+          // so the element index is read off the lane bits from the top
+          int e;
+          const double v = reduce_scatter<2 * MS>(a, lane, e) * pscale;
+          // after log2(2 MS) halvings the surviving lanes are those with the low (5 - log2(2 MS)) bits arbitrary: let the
+          // lane whose low bits are zero write
+          constexpr int LOWBITS = 5 - (MS == 8 ? 4 : MS == 4 ? 3 : MS == 2 ? 2 : 1);
+          if ((lane & ((1 << LOWBITS) - 1)) == 0) {
+            const int j = e >> 1, ri = e & 1;
+            if (j < m) {
+              double* dv = reinterpret_cast<double*>(&vn[vidx(j, row)]);
+              dv[ri] = v;
+              double* dp = reinterpret_cast<double*>(&psi_b[(size_t)(step + 1) * mn + (size_t)j * n + row]);
+              dp[ri] = v;
+            }
+          }
+        }
+      }
+      cur ^= 1;
+    }
+  } else {
+    const int sg = tid >> 7, cp = tid & 127;               // state pair, column pair (columns 2 cp, 2 cp + 1)
+    const bool act = 2 * sg < m && 2 * cp < ld;
+    for (int step = 0; step < nsteps; ++step) {
+      const int t = T - 1 - step;
+      const cplx* vc = vecs + (size_t)cur * 8 * ld;
+      cplx* vn = vecs + (size_t)(cur ^ 1) * 8 * ld;
+      double a[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};      // [state][col][re/im]
+      for (int c = 0; c < NC; ++c, ++g) {
+        __syncthreads();                                   // previous chunk's stage is free (and, for c = 0, v(cur) complete)
+        if (tid == 0) prefetch(g + NST - 1);
+        while (!mbar_try_wait(&full[g % NST], (uint32_t)(g / NST) & 1u)) {}
+        const __half* St = ring + (size_t)(g % NST) * stage_halfs;
+        const int rows = min(R, n - c * R);
+        if (act) {
+          const uint32_t* w0 = reinterpret_cast<const uint32_t*>(St) + cp;
+          const size_t pw = (size_t)R * lh;                // plane stride in 32-bit words
+          for (int rr = 0; rr < rows; ++rr) {
+            const uint32_t* wr = w0 + (size_t)rr * lh;
+            const double2 er = widen2(wr[0], wr[pw]);      // Re of columns 2cp, 2cp+1
+            const double2 ei = widen2(wr[2 * pw], wr[3 * pw]);
+            const int r = c * R + rr;
+            const cplx x = vc[vidx(2 * sg, r)], y = vc[vidx(2 * sg + 1, r)];
+            // conj(e) * lambda = (er x.x + ei x.y) + i (er x.y - ei x.x)
+            a[0][0][0] = fma(er.x, x.x, a[0][0][0]); a[0][0][0] = fma(ei.x, x.y, a[0][0][0]);
+            a[0][0][1] = fma(er.x, x.y, a[0][0][1]); a[0][0][1] = fma(-ei.x, x.x, a[0][0][1]);
+            a[0][1][0] = fma(er.y, x.x, a[0][1][0]); a[0][1][0] = fma(ei.y, x.y, a[0][1][0]);
+            a[0][1][1] = fma(er.y, x.y, a[0][1][1]); a[0][1][1] = fma(-ei.y, x.x, a[0][1][1]);
+            a[1][0][0] = fma(er.x, y.x, a[1][0][0]); a[1][0][0] = fma(ei.x, y.y, a[1][0][0]);
+            a[1][0][1] = fma(er.x, y.y, a[1][0][1]); a[1][0][1] = fma(-ei.x, y.x, a[1][0][1]);
+            a[1][1][0] = fma(er.y, y.x, a[1][1][0]); a[1][1][0] = fma(ei.y, y.y, a[1][1][0]);
+            a[1][1][1] = fma(er.y, y.y, a[1][1][1]); a[1][1][1] = fma(-ei.y, y.x, a[1][1][1]);
+          }
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int js = 0; js < 2; ++js)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int j = 2 * sg + js, col = 2 * cp + cc;
+            if (j < m && col < n) {
+              cplx v = make_double2(a[js][cc][0] * pscale, a[js][cc][1] * pscale);
+              const cplx s = source(t, j, col);
+              v.x += s.x; v.y += s.y;
+              vn[vidx(j, col)] = v;
+              lam_b[(size_t)t * mn + (size_t)j * n + col] = v;
+            }
+          }
+      }
+      cur ^= 1;
+    }
+  }
+}
+
+}  // namespace
+
+bool qoc_plane_sweep_supported(int n, int m) {
+  if (n > TC_MAX_N || m > 8) return false;
+  return plane_sweep_shape(n, m).nst >= 2;
+}
+
+template <bool REV, int MS>
+static cudaError_t launch_ps(const QocParams& p, const void* planes, const PlaneSweepShape& s, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_plane_sweep<REV, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+  if (e != cudaSuccess) return e;
+  k_plane_sweep<REV, MS><<<p.B, NTH, s.smem, st>>>(p, reinterpret_cast<const __half*>(planes), s.nst);
+  return cudaGetLastError();
+}
+
+cudaError_t qoc_launch_plane_sweep(const QocParams& p, const void* planes, int reverse, cudaStream_t st, int64_t* launches) {
+  if (!qoc_plane_sweep_supported(p.n, p.m)) return cudaErrorNotSupported;
+  ++*launches;
+  const PlaneSweepShape s = plane_sweep_shape(p.n, p.m);
+  if (reverse) return launch_ps<true, 8>(p, planes, s, st);
+  if (p.m <= 2) return launch_ps<false, 2>(p, planes, s, st);
+  if (p.m <= 4) return launch_ps<false, 4>(p, planes, s, st);
+  return launch_ps<false, 8>(p, planes, s, st);
+}

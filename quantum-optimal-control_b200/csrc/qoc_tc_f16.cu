@@ -1,0 +1,679 @@
+// tcgen05 / TMEM / TMA complex-GEMM program engine: the fp32-class (QOC_F16X2) arithmetic of the
+// propagator stage (get_matexp / matexp_op, core/tensorflow_state.py:25-46,70-75) and of the
+// U_final chain (init_tf_propagator, :204-227) for Hilbert dimensions up to 256.
+//
+// One persistent CTA runs "items"; an item is a sequence of DEPENDENT complex n x n products
+// (Taylor / Paterson-Stockmeyer steps and squarings of one (b,t); the 15 products of one chain segment;
+// the segment chain of one instance).  Matrices live in global memory (L2-resident scratch or the
+// propagator cache in HBM) as split fp16 plane sets (qoc_tc_f16.cuh); a product D = A B is
+//     Dr = Ar Br - Ai Bi,  Di = Ar Bi + Ai Br,   each real product = 3 MMAs (h0 h0 + h0 h1 + h1 h0),
+// i.e. 12 tcgen05.mma.kind::f16 (M = 128, N = n16, K = 16) per 16 columns of K, accumulated in fp32 in
+// TMEM (Dr in columns [0,N), Di in [N,2N)); the sign of the Ai Bi term is the descriptor's negate-A bit.
+//
+// Roles (320 threads):
+//   warp 0     TMA producer: per 32-wide k-block, four A-plane boxes {32 k x 128 rows} (K-major, SWIZZLE_64B)
+//              and 4 x NG B-plane boxes {64 n x 32 k} (MN-major, SWIZZLE_128B: B is read in its row-major
+//              storage, no transposed copy exists anywhere) into a ring of stages; out-of-range rows /
+//              columns are zero-filled by the 3-D tensor maps (dims {n, n, planes}).
+//   warp 1     MMA issuer: waits full[s], issues 24 MMAs per stage, tcgen05.commit -> empty[s]; after the
+//              last k-block commit -> tmem_full.
+//   warps 2-9  epilogue (two per TMEM lane quarter, even / odd 16-column chunks): tcgen05.ld the accumulator rows (thread = row), apply  c0 D + c1 X + c2 I,
+//              re-split into h0/h1 and store the plane set(s) of the result straight to global memory
+//              (each thread writes whole 32-byte sectors of its row); fence.proxy.async + arrive on op_done
+//              so the producer may fetch the result as an operand of the next product.
+// Every mbarrier wait carries a clock64 timeout that flags err_flag instead of hanging the GPU.
+#include "qoc_tc_f16.cuh"
+#include <math.h>
+#include <string.h>
+#include <stdio.h>
+
+#define DEVINL __device__ __forceinline__
+
+namespace {
+
+constexpr int KB_ELEMS = 32;                     // K elements per stage
+constexpr uint32_t A_PLANE_BYTES = 128 * 64;     // box {32 halfs, 128 rows}
+constexpr uint32_t B_GROUP_BYTES = 32 * 128;     // box {64 halfs, 32 rows}
+constexpr int NEPI = 256;                        // epilogue threads (8 warps: two per TMEM lane quarter)
+constexpr int NTHREADS = 64 + NEPI;
+constexpr int MAX_STAGES = 4;
+constexpr long long TIMEOUT_CYCLES = 4000000000LL;
+
+DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVINL void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// false = timed out (or another role already failed): the caller unwinds to the teardown
+DEVINL bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* dead) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*dead || clock64() - t0 > TIMEOUT_CYCLES) { *dead = 1; return false; }
+  }
+  return true;
+}
+DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+DEVINL void mma_f16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DEVINL void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&u)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+}
+DEVINL uint32_t elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(e));
+  return e;
+}
+DEVINL void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor layout): start >> 4 | LBO >> 4 << 16 |
+// SBO >> 4 << 32 | version 1 << 46 | layout type << 61 (SWIZZLE_128B = 2, SWIZZLE_64B = 4)
+DEVINL uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+
+// resolved operands of one product
+struct OpR {
+  int a_cls, b_cls, e_cls, d1_cls, d2_cls;       // -1 = none
+  long long a_idx, b_idx, e_idx, d1_idx, d2_idx; // matrix index within the class
+  float c1[3], c2[3];
+  int f64out;                                    // last product of a CHAIN item: write U_final, unitary_scale
+};
+
+DEVINL int item_nops(const TcParams& q, long long item) {
+  switch (q.prog) {
+    case TC_PROG_EXPM: return q.nops;
+    case TC_PROG_SEG: {
+      const int sg = (int)(item % q.S);
+      const int t0 = sg * q.L, t1 = min(q.T, t0 + q.L);
+      return max(1, t1 - t0 - 1);
+    }
+    case TC_PROG_CHAIN: return q.chain_len;
+    default: return 1;
+  }
+}
+
+DEVINL void make_op(const TcParams& q, long long item, int j, int nops, OpR& o) {
+  const long long sb = (long long)blockIdx.x * TC_NSLOT;
+  const float cu = 1.0f / (float)(1 << TC_EU);   // unitary x unitary -> unitary scale
+  o.e_cls = -1; o.d2_cls = -1; o.d1_cls = -1; o.f64out = 0;
+  o.e_idx = o.d1_idx = o.d2_idx = 0;
+  o.c1[0] = cu; o.c1[1] = 0.f; o.c1[2] = 0.f;
+  o.c2[0] = o.c2[1] = o.c2[2] = 0.f;
+  switch (q.prog) {
+    case TC_PROG_EXPM: {
+      const TcExpmOp e = q.ops[j];
+      o.a_cls = TC_CLS_SCR; o.a_idx = sb + e.sa;
+      o.b_cls = TC_CLS_SCR; o.b_idx = sb + e.sb;
+      o.e_cls = TC_CLS_SCR; o.e_idx = sb + e.se;
+      if (e.d1 >= 0) {
+        if (e.d1 == TC_SLOT_OUT) { o.d1_cls = TC_CLS_P; o.d1_idx = item; } else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + e.d1; }
+      }
+      if (e.d2 >= 0) {
+        if (e.d2 == TC_SLOT_OUT) { o.d2_cls = TC_CLS_P; o.d2_idx = item; } else { o.d2_cls = TC_CLS_SCR; o.d2_idx = sb + e.d2; }
+      }
+      for (int i = 0; i < 3; ++i) { o.c1[i] = e.c1[i]; o.c2[i] = e.c2[i]; }
+      break;
+    }
+    case TC_PROG_SEG: {
+      const long long b = item / q.S;
+      const int sg = (int)(item % q.S);
+      const int t0 = sg * q.L, t1 = min(q.T, t0 + q.L);
+      const long long pb = b * q.T;
+      if (t1 - t0 == 1) {                          // single propagator: multiply by the identity (CONST 1)
+        o.a_cls = TC_CLS_P; o.a_idx = pb + t0; o.b_cls = TC_CLS_CONST; o.b_idx = 1;
+      } else {
+        o.a_cls = TC_CLS_P; o.a_idx = pb + t0 + j + 1;
+        if (j == 0) { o.b_cls = TC_CLS_P; o.b_idx = pb + t0; } else { o.b_cls = TC_CLS_SCR; o.b_idx = sb + ((j - 1) & 1); }
+      }
+      if (j == nops - 1) { o.d1_cls = TC_CLS_SEG; o.d1_idx = item; } else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + (j & 1); }
+      break;
+    }
+    case TC_PROG_CHAIN: {
+      o.a_cls = q.chain_cls; o.a_idx = item * q.chain_len + j;
+      if (j == 0) { o.b_cls = TC_CLS_CONST; o.b_idx = 0; } else { o.b_cls = TC_CLS_SCR; o.b_idx = sb + ((j - 1) & 1); }
+      if (j == nops - 1) o.f64out = 1; else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + (j & 1); }
+      break;
+    }
+    default: {
+      o.a_cls = TC_CLS_P; o.a_idx = 2 * item; o.b_cls = TC_CLS_P; o.b_idx = 2 * item + 1;
+      o.d1_cls = TC_CLS_SEG; o.d1_idx = item;
+      break;
+    }
+  }
+}
+
+// x (stored units) -> fp16 pair
+DEVINL void split2(float a, float b, uint32_t& h0, uint32_t& h1) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(x);
+  const __half2 y = __floats2half2_rn(a - f.x, b - f.y);
+  h0 = *reinterpret_cast<const uint32_t*>(&x);
+  h1 = *reinterpret_cast<const uint32_t*>(&y);
+}
+// 16 consecutive columns of one row: 32 bytes (one L2 sector) per plane, 256-bit accesses
+DEVINL void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+DEVINL void ldg256(const void* p, uint32_t (&r)[8]) {     // L2-coherent (.cg): the data was written by this CTA moments ago
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p)
+               : "memory");
+}
+DEVINL void store_planes16(__half* mat, size_t plane, int ld, int row, int col, const float (&re)[16], const float (&im)[16]) {
+  uint32_t a0[8], a1[8], b0[8], b1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { split2(re[2 * i], re[2 * i + 1], a0[i], a1[i]); split2(im[2 * i], im[2 * i + 1], b0[i], b1[i]); }
+  __half* p0 = mat + (size_t)row * ld + col;
+  stg256(p0, a0);
+  stg256(p0 + plane, a1);
+  stg256(p0 + 2 * plane, b0);
+  stg256(p0 + 3 * plane, b1);
+}
+DEVINL void unpack16(const uint32_t (&h0)[8], const uint32_t (&h1)[8], float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&h0[i]));
+    const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&h1[i]));
+    v[2 * i] = fa.x + fb.x; v[2 * i + 1] = fa.y + fb.y;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const __grid_constant__ TcMaps maps) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull, bar_tempty, bar_opdone;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int dead_s;
+  __shared__ float wts[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = q.n, ld = q.ld, N16 = q.N16, NP32 = q.NP32, NG = q.NG, RB = q.RB, KBLK = q.KBLK, NS = q.stages;
+  const uint32_t b_plane_bytes = (uint32_t)NG * B_GROUP_BYTES;
+  const uint32_t stage_bytes = 4 * A_PLANE_BYTES + 4 * b_plane_bytes;
+  const size_t plane = (size_t)n * ld, mat = 4 * plane;
+  unsigned char* jtile = smem + (size_t)NS * stage_bytes;            // [32 k][64 n] fp16, MN-major SWIZZLE_128B: jval on the diagonal
+  long long t_wait0 = 0, t_wait1 = 0, t_work = 0;                    // per-role cycle counters (q.prof)
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_tfull, 1);
+    mbar_init(&bar_tempty, NEPI);
+    mbar_init(&bar_opdone, NEPI);
+    dead_s = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 32 * 64; i += NTHREADS) {                    // J[k][nn] = jval * delta(k, nn)
+    const int k = i >> 6, nn = i & 63;
+    const uint32_t off = (uint32_t)(k * 128 + ((((nn >> 3) ^ (k & 7))) << 4) + (nn & 7) * 2);
+    *reinterpret_cast<__half*>(jtile + off) = __float2half(nn == k ? q.jval : 0.0f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)q.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t taddr = *(volatile uint32_t*)&tmem_base_s;
+  volatile int* dead = &dead_s;
+  const bool prof = q.prof != nullptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, done_cnt = 0;               // stage-use counter, op_done phase counter
+      for (long long item = blockIdx.x; item < q.items && !*dead; item += gridDim.x) {
+        const int nops = item_nops(q, item);
+        for (int j = 0; j < nops && !*dead; ++j) {
+          OpR o; make_op(q, item, j, nops, o);
+          // scratch operands (and X built by the prologue) must be complete: one op_done phase per product, plus one
+          // per item prologue (EXPM).  Operands from other classes were written by an earlier kernel.
+          const bool need = (q.prog == TC_PROG_EXPM) || j > 0;
+          if (need) {
+            const long long c0 = prof ? clock64() : 0;
+            if (!mbar_wait(&bar_opdone, done_cnt & 1, dead)) break;
+            ++done_cnt;
+            if (prof) t_wait0 += clock64() - c0;
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const CUtensorMap* ma = &maps.a[o.a_cls];
+          const CUtensorMap* mb = &maps.b[o.b_cls];
+          const int za = (int)(o.a_idx * 4), zb = (int)(o.b_idx * 4);
+          for (int rb = 0; rb < RB && !*dead; ++rb) {
+            for (int kb = 0; kb < KBLK; ++kb, ++it) {
+              const int s = it % NS;
+              const long long c0 = prof ? clock64() : 0;
+              if (!mbar_wait(&bar_empty[s], ((it / NS) & 1) ^ 1, dead)) break;
+              if (prof) t_wait1 += clock64() - c0;
+              mbar_expect_tx(&bar_full[s], stage_bytes);
+              const uint32_t sa = smem_u32(smem) + s * stage_bytes, sbb = sa + 4 * A_PLANE_BYTES;
+#pragma unroll
+              for (int pl = 0; pl < 4; ++pl) tma_load_3d(sa + pl * A_PLANE_BYTES, ma, kb * KB_ELEMS, rb * 128, za + pl, &bar_full[s]);
+              for (int pl = 0; pl < 4; ++pl)
+                for (int g = 0; g < NG; ++g)
+                  tma_load_3d(sbb + pl * b_plane_bytes + g * B_GROUP_BYTES, mb, g * 64, kb * KB_ELEMS, zb + pl, &bar_full[s]);
+            }
+          }
+        }
+        {   // consume the op_done phase of the item's last product
+          if (*dead || !mbar_wait(&bar_opdone, done_cnt & 1, dead)) break;
+          ++done_cnt;
+        }
+      }
+      if (prof) { q.prof[(size_t)blockIdx.x * 8 + 0] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 1] = t_wait1; }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(N16 >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A/B f16, A K-major, B MN-major
+    const uint32_t idesc_na = idesc | (1u << 13);                                                          // negate A
+    const uint32_t idesc_j = (1u << 4) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);            // N = 32 (J tile)
+    const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
+    const uint32_t sj = sbase + NS * stage_bytes;
+    uint32_t it = 0, acc_cnt = 0;
+    bool ok = true;
+    for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
+      const int nops = item_nops(q, item);
+      for (int j = 0; j < nops && ok; ++j) {
+        const bool usej = q.prog == TC_PROG_EXPM && q.ops[j].usej;
+        for (int rb = 0; rb < RB && ok; ++rb, ++acc_cnt) {
+          long long c0 = prof ? clock64() : 0;
+          ok = __all_sync(0xffffffffu, mbar_wait(&bar_tempty, (acc_cnt & 1) ^ 1, dead));   // accumulators drained by the epilogue
+          if (!ok) break;
+          if (prof) t_wait0 += clock64() - c0;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kb = 0; kb < KBLK && ok; ++kb, ++it) {
+            const int s = it % NS;
+            c0 = prof ? clock64() : 0;
+            ok = __all_sync(0xffffffffu, mbar_wait(&bar_full[s], (it / NS) & 1, dead));
+            if (!ok) break;
+            if (prof) t_wait1 += clock64() - c0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint32_t sa = sbase + s * stage_bytes, sbb = sa + 4 * A_PLANE_BYTES;
+#pragma unroll
+              for (int k16 = 0; k16 < 2; ++k16) {
+                uint64_t da[4], db[4];
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) {
+                  da[pl] = make_desc(sa + pl * A_PLANE_BYTES + k16 * 32, q.a_lbo, q.a_sbo, 4);
+                  db[pl] = make_desc(sbb + pl * b_plane_bytes + k16 * 2048, q.b_lbo, q.b_sbo, 2);
+                }
+                const uint32_t first = (kb == 0 && k16 == 0) ? 0u : 1u;
+                const uint32_t dr = tbase, di = tbase + (uint32_t)NP32;
+                // planes: 0 = Re h0, 1 = Re h1, 2 = Im h0, 3 = Im h1
+                mma_f16_ss(dr, da[0], db[1], idesc, first);             // Ar0 Br1
+                mma_f16_ss(dr, da[1], db[0], idesc, 1u);                // Ar1 Br0
+                mma_f16_ss(dr, da[2], db[3], idesc_na, 1u);             // -Ai0 Bi1
+                mma_f16_ss(dr, da[3], db[2], idesc_na, 1u);             // -Ai1 Bi0
+                mma_f16_ss(dr, da[0], db[0], idesc, 1u);                // Ar0 Br0
+                mma_f16_ss(dr, da[2], db[2], idesc_na, 1u);             // -Ai0 Bi0
+                mma_f16_ss(di, da[0], db[3], idesc, first);             // Ar0 Bi1
+                mma_f16_ss(di, da[1], db[2], idesc, 1u);                // Ar1 Bi0
+                mma_f16_ss(di, da[2], db[1], idesc, 1u);                // Ai0 Br1
+                mma_f16_ss(di, da[3], db[0], idesc, 1u);                // Ai1 Br0
+                mma_f16_ss(di, da[0], db[2], idesc, 1u);                // Ar0 Bi0
+                mma_f16_ss(di, da[2], db[0], idesc, 1u);                // Ai0 Br0
+                if (usej) {                                             // D[:, 32 kb + c] += jval * A[:, 32 kb + c]
+                  const uint64_t dj = make_desc(sj + k16 * 2048, q.b_lbo, q.b_sbo, 2);
+                  const uint32_t cj = (uint32_t)(kb * 32);
+                  mma_f16_ss(dr + cj, da[1], dj, idesc_j, 1u);
+                  mma_f16_ss(dr + cj, da[0], dj, idesc_j, 1u);
+                  mma_f16_ss(di + cj, da[3], dj, idesc_j, 1u);
+                  mma_f16_ss(di + cj, da[2], dj, idesc_j, 1u);
+                }
+              }
+              umma_commit(&bar_empty[s]);
+              if (kb == KBLK - 1) umma_commit(&bar_tfull);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (prof && lane == 0) { q.prof[(size_t)blockIdx.x * 8 + 2] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 3] = t_wait1; }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;              // which of the two warps of this lane quarter: even / odd 16-column chunks
+    const int et = (warp - 2) * 32 + lane;
+    const int lrow = qd * 32 + lane;
+    const uint32_t lane_addr = taddr + ((uint32_t)(qd * 32) << 16);
+    uint32_t acc_cnt = 0;
+    bool ok = true;
+    for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
+      const int nops = item_nops(q, item);
+      if (q.prog == TC_PROG_EXPM) {
+        // X' = xscale (A_0 + sum_k u_k A_k), u_k = maxA_k sin(base[b][k][t])  (init_tf_ops_weight, :168-185)
+        const long long b = item / q.T;
+        const int t = (int)(item % q.T);
+        if (et <= q.K) wts[et] = et == 0 ? q.xscale : (float)(q.maxA[et - 1] * sin(q.ctrl[((size_t)b * q.K + et - 1) * q.T + t])) * q.xscale;
+        epi_bar();
+        __half* X = q.base[TC_CLS_SCR] + (size_t)((long long)blockIdx.x * TC_NSLOT) * mat;
+        const int l16 = ld >> 4;
+        const size_t nn = (size_t)n * n;
+        for (int i16 = et; i16 < n * l16; i16 += NEPI) {
+          const int r = i16 / l16, c16 = (i16 - r * l16) * 16;
+          float re[16], im[16];
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) {
+            float xr = 0.f, xi = 0.f;
+            if (c16 + cc < n) {
+              for (int k = 0; k <= q.K; ++k) {
+                const float2 a = __ldg(q.A_f + (size_t)k * nn + (size_t)r * n + c16 + cc);
+                xr = fmaf(wts[k], a.x, xr); xi = fmaf(wts[k], a.y, xi);
+              }
+            }
+            re[cc] = xr; im[cc] = xi;
+          }
+          store_planes16(X, plane, ld, r, c16, re, im);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_arrive(&bar_opdone);
+        epi_bar();                                   // X is read back (elementwise source) by other threads than its writers
+      } else if (q.prog == TC_PROG_CHAIN) {
+        if (et == 0) q.scal[(size_t)item * 8 + 5] = 0.0;
+        epi_bar();
+      }
+      for (int j = 0; j < nops && ok; ++j) {
+        OpR o; make_op(q, item, j, nops, o);
+        const __half* E = o.e_cls >= 0 ? q.base[o.e_cls] + (size_t)o.e_idx * mat : nullptr;
+        __half* D1 = o.d1_cls >= 0 ? q.base[o.d1_cls] + (size_t)o.d1_idx * mat : nullptr;
+        __half* D2 = o.d2_cls >= 0 ? q.base[o.d2_cls] + (size_t)o.d2_idx * mat : nullptr;
+        const bool useE = E && (o.c1[1] != 0.f || o.c2[1] != 0.f);
+        for (int rb = 0; rb < RB && ok; ++rb, ++acc_cnt) {
+          const int row = rb * 128 + lrow;
+          const bool vrow = row < n;
+          // elementwise source of the first chunk, fetched while the MMAs still run
+          uint32_t eraw[4][8];
+          const bool ldE = useE && vrow;
+          auto fetchE = [&](int c0) {
+            if (ldE) {
+              const __half* p0 = E + (size_t)row * ld + c0;
+#pragma unroll
+              for (int pl = 0; pl < 4; ++pl) ldg256(p0 + pl * plane, eraw[pl]);
+            }
+          };
+          fetchE(16 * half);
+          long long c0t = prof ? clock64() : 0;
+          ok = __all_sync(0xffffffffu, mbar_wait(&bar_tfull, acc_cnt & 1, dead));
+          if (!ok) break;
+          if (prof) { const long long c1t = clock64(); t_wait0 += c1t - c0t; c0t = c1t; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          double sr = 0.0, si = 0.0;                 // row sum of the final product (unitary_scale)
+          for (int c0 = 16 * half; c0 < N16; c0 += 32) {
+            uint32_t ur[16], ui[16];
+            tmem_ld16(lane_addr + (uint32_t)c0, ur);
+            tmem_ld16(lane_addr + (uint32_t)(NP32 + c0), ui);
+            float er[16], ei[16];
+            if (useE) { unpack16(eraw[0], eraw[1], er); unpack16(eraw[2], eraw[3], ei); }
+            else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) er[i] = ei[i] = 0.f;
+            }
+            if (c0 + 32 < N16) fetchE(c0 + 32);      // next chunk's source in flight behind this chunk's arithmetic
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!vrow) continue;
+            float dr[16], di[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { dr[i] = __uint_as_float(ur[i]); di[i] = __uint_as_float(ui[i]); }
+            if (D1) {
+              float orr[16], oi[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                orr[i] = fmaf(o.c1[0], dr[i], o.c1[1] * er[i]) + ((c0 + i == row) ? o.c1[2] : 0.f);
+                oi[i] = fmaf(o.c1[0], di[i], o.c1[1] * ei[i]);
+              }
+              store_planes16(D1, plane, ld, row, c0, orr, oi);
+            }
+            if (D2) {
+              float orr[16], oi[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                orr[i] = fmaf(o.c2[0], dr[i], o.c2[1] * er[i]) + ((c0 + i == row) ? o.c2[2] : 0.f);
+                oi[i] = fmaf(o.c2[0], di[i], o.c2[1] * ei[i]);
+              }
+              store_planes16(D2, plane, ld, row, c0, orr, oi);
+            }
+            if (o.f64out) {
+              const double sc = 1.0 / ((double)(1 << TC_EU) * (double)(1 << TC_EU));
+              double2* U = q.Ufin + (size_t)item * n * n + (size_t)row * n;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < n) {
+                  const double xr = (double)dr[i] * sc, xi = (double)di[i] * sc;
+                  U[c0 + i] = make_double2(xr, xi);
+                  sr += xr; si += xi;
+                }
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&bar_tempty);
+          if (o.f64out) {
+            // unitary_scale = (1/n) sum_r |sum_c X_rc|^2  (init_tf_propagator, tensorflow_state.py:225 on the real embedding);
+            // the two warps of a lane quarter hold the even / odd column chunks of the same rows
+            __shared__ double rs[2][128][2];
+            rs[half][lrow][0] = sr; rs[half][lrow][1] = si;
+            epi_bar();
+            if (half == 0) {
+              const double tr = rs[0][lrow][0] + rs[1][lrow][0], ti = rs[0][lrow][1] + rs[1][lrow][1];
+              double v = vrow ? (tr * tr + ti * ti) / (double)n : 0.0;
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+              if (lane == 0) atomicAdd(&q.scal[(size_t)item * 8 + 5], v);
+            }
+            epi_bar();
+          }
+          if (rb == RB - 1) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_arrive(&bar_opdone);
+          }
+          if (prof) t_work += clock64() - c0t;
+        }
+      }
+    }
+    if (prof && et == 0) { q.prof[(size_t)blockIdx.x * 8 + 4] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 5] = t_work; }
+  }
+  // ---------------------------------------------------------------------- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (dead_s && tid == 0 && q.err_flag) atomicExch(q.err_flag, 1);
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)q.tmem_cols) : "memory");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host side
+
+bool tc_geometry(int n, TcGeom* g) {
+  if (n < 1 || n > TC_MAX_N) return false;
+  g->n = n;
+  g->ld = tc_ld(n);
+  g->N16 = (n + 15) / 16 * 16;
+  g->NP32 = (n + 31) / 32 * 32;
+  g->NG = (g->N16 + 63) / 64;
+  g->RB = n > 128 ? 2 : 1;
+  g->KBLK = (n + KB_ELEMS - 1) / KB_ELEMS;
+  int cols = 32;
+  while (cols < 2 * g->NP32) cols *= 2;
+  g->tmem_cols = cols;
+  const size_t stage = 4 * (size_t)A_PLANE_BYTES + 4 * (size_t)g->NG * B_GROUP_BYTES;
+  const size_t budget = 225 * 1024;
+  g->ctas_per_sm = (n <= 64) ? 2 : 1;
+  int st = (int)((budget / g->ctas_per_sm - 2048 - 4096) / stage);
+  if (st > MAX_STAGES) st = MAX_STAGES;
+  if (st < 1) return false;
+  g->stages = st;
+  g->smem = (size_t)st * stage + 4096 + 1024;
+  g->mat_halfs = (size_t)4 * n * g->ld;
+  return true;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+const char* tc_make_map(CUtensorMap* map, const void* base, int n, int ld, unsigned long long n_mats, bool b_form) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p ||
+        qr != cudaDriverEntryPointSuccess)
+      return "cuTensorMapEncodeTiled is not available from the driver";
+    fn = (PFN_encodeTiled)p;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)(4ull * n_mats)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)n * ld * 2};
+  const cuuint32_t box_a[3] = {KB_ELEMS, 128, 1}, box_b[3] = {64, KB_ELEMS, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, b_form ? box_b : box_a, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, b_form ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    static char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return msg;
+  }
+  return nullptr;
+}
+
+void tc_pick_scales(double xmax, double theta, int* eX, int* eY) {
+  // stored magnitudes stay below 2^14 = 16384 (fp16 overflows at 65504)
+  auto pick = [](double bound) {
+    if (!(bound > 0.0)) bound = 1e-30;
+    int e = (int)floor(14.0 - log2(bound));
+    if (e > 60) e = 60;
+    if (e < -20) e = -20;
+    return e;
+  };
+  *eX = pick(xmax);
+  *eY = pick(theta * theta);
+}
+
+void tc_build_expm_ops(int p, int s, int eX, int eY, std::vector<TcExpmOp>& ops) {
+  // S = sum_{j<=p} X^j/j! = sum_{i<=J} Y^i (a_i I + b_i X), Y = X^2, a_i = 1/(2i)!, b_i = 1/(2i+1)! (b_J = 0 for even p),
+  // evaluated by Horner in Y (Paterson-Stockmeyer, block 2); then s squarings.  Slots: 0 = X, 1 = Y, 2/3 = Z ping-pong.
+  ops.clear();
+  double fact[64];
+  fact[0] = 1.0;
+  for (int i = 1; i < 64; ++i) fact[i] = fact[i - 1] * (double)i;
+  const int J = p / 2;
+  auto a = [&](int i) { return 1.0 / fact[2 * i]; };
+  auto b = [&](int i) { return (2 * i + 1 <= p) ? 1.0 / fact[2 * i + 1] : 0.0; };
+  const double sU = ldexp(1.0, TC_EU);
+  auto clear = [](TcExpmOp& o) { memset(&o, 0, sizeof(o)); o.d1 = o.d2 = -1; };
+  TcExpmOp o;
+  clear(o);
+  o.sa = 0; o.sb = 0;                                     // D = X X  (units 2^(2 eX))
+  o.d1 = 1; o.c1[0] = (float)ldexp(1.0, eY - 2 * eX);     // Y
+  o.d2 = 2;                                               // first Horner value Z
+  int next_j;
+  if ((p & 1) == 0 && J >= 1) {                           // Z = a_J Y + b_{J-1} X + a_{J-1} I
+    o.c2[0] = (float)(a(J) * ldexp(1.0, TC_EU - 2 * eX));
+    o.c2[1] = (float)(b(J - 1) * ldexp(1.0, TC_EU - eX));
+    o.c2[2] = (float)(a(J - 1) * sU);
+    next_j = J - 2;
+  } else {                                                // Z = b_J X + a_J I
+    o.c2[0] = 0.f;
+    o.c2[1] = (float)(b(J) * ldexp(1.0, TC_EU - eX));
+    o.c2[2] = (float)(a(J) * sU);
+    next_j = J - 1;
+  }
+  ops.push_back(o);
+  int cur = 2;
+  // With squarings the program tracks E = P - I instead of P: (I + E)^2 = I + (2E + E^2).  The identity never enters a
+  // tensor-core accumulation, so the accumulator's truncation error is relative to |E^2| (tiny for the early, most
+  // amplified squarings) instead of to the O(1) diagonal -- the fp32 analogue of an expm1-style squaring phase.
+  const bool eform = s > 0;
+  if (eform && next_j < 0) ops.back().c2[2] -= (float)sU;       // no Horner step: the first value already is S
+  for (int j = next_j; j >= 0; --j) {                     // Z <- Z Y + b_j X + a_j I
+    clear(o);
+    o.sa = (int8_t)cur; o.sb = 1;
+    o.d1 = (int8_t)(cur ^ 1);
+    o.c1[0] = (float)ldexp(1.0, -eY);
+    o.c1[1] = (float)(b(j) * ldexp(1.0, TC_EU - eX));
+    o.c1[2] = (float)((a(j) - ((eform && j == 0) ? 1.0 : 0.0)) * sU);
+    ops.push_back(o);
+    cur ^= 1;
+  }
+  for (int i = 0; i < s; ++i) {                           // E <- 2 E + E E   (+ I after the last one)
+    clear(o);
+    o.sa = o.sb = o.se = (int8_t)cur;                     // 2E is added by the epilogue in fp32 round-to-nearest (riding it on
+    o.d1 = (int8_t)(cur ^ 1);                             // the MMA stream through the J tile -- usej -- costs a decade of accuracy:
+    o.c1[0] = (float)ldexp(1.0, -TC_EU);                  // the accumulator then holds |2E| during every truncating accumulation)
+    o.c1[1] = 2.0f;
+    o.c1[2] = (i == s - 1) ? (float)sU : 0.0f;
+    ops.push_back(o);
+    cur ^= 1;
+  }
+  // the last value goes to the propagator cache instead of a scratch slot
+  TcExpmOp& last = ops.back();
+  if (ops.size() == 1) last.d2 = TC_SLOT_OUT; else last.d1 = TC_SLOT_OUT;
+}
+
+void tc_pack_host(const double* z, int n, int ld, int e, __half* out) {
+  const double sc = ldexp(1.0, e);
+  const size_t plane = (size_t)n * ld;
+  for (size_t i = 0; i < 4 * plane; ++i) out[i] = __float2half(0.f);
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c)
+      for (int ri = 0; ri < 2; ++ri) {
+        const float v = (float)(z[((size_t)r * n + c) * 2 + ri] * sc);
+        const __half h0 = __float2half_rn(v);
+        const __half h1 = __float2half_rn(v - __half2float(h0));
+        out[(size_t)(2 * ri) * plane + (size_t)r * ld + c] = h0;
+        out[(size_t)(2 * ri + 1) * plane + (size_t)r * ld + c] = h1;
+      }
+}
+
+cudaError_t tc_launch(const TcParams& q_in, const TcMaps& maps, const TcGeom& g, int grid, cudaStream_t st) {
+  TcParams q = q_in;
+  q.n = g.n; q.ld = g.ld; q.N16 = g.N16; q.NP32 = g.NP32; q.NG = g.NG; q.RB = g.RB; q.KBLK = g.KBLK; q.stages = g.stages; q.tmem_cols = g.tmem_cols;
+  if (!q.a_sbo) { q.a_lbo = 1; q.a_sbo = 512 >> 4; }                    // K-major SWIZZLE_64B: 8-row groups 512 B apart
+  if (!q.b_sbo) { q.b_lbo = B_GROUP_BYTES >> 4; q.b_sbo = 1024 >> 4; }  // MN-major SWIZZLE_128B: n-groups 4096 B, k-atoms 1024 B
+  if (q.jval == 0.f) q.jval = (float)(1 << (TC_EU + 1));
+  cudaError_t e = cudaFuncSetAttribute(k_tc_prog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return e;
+  if (grid < 1) grid = 1;
+  k_tc_prog<<<grid, NTHREADS, g.smem, st>>>(q, maps);
+  return cudaGetLastError();
+}

@@ -12,9 +12,11 @@ import numpy as np
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libqoc_b200.so")
 
-QOC_F64, QOC_TF32X3 = 0, 1
+QOC_F64, QOC_TF32X3, QOC_F16X2 = 0, 1, 2
 QOC_FLAG_STATE_TRANSFER = 1
-_DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF32X3}
+QOC_ABI_VERSION = 2          # include/qoc_b200.h
+# 'f16x2': fp32-class tcgen05 / TMA path (n <= 256, m <= 8): the reference's own working precision is float32
+_DTYPES = {'f64': QOC_F64, 'fp64': QOC_F64, 'float64': QOC_F64, 'tf32x3': QOC_TF32X3, 'f16x2': QOC_F16X2}
 
 SYMBOLS = ["qoc_abi_version", "qoc_create", "qoc_destroy", "qoc_last_error", "qoc_workspace_bytes",
            "qoc_set_workspace", "qoc_set_problem", "qoc_set_regularizers", "qoc_value_and_grad", "qoc_evolve",
@@ -55,6 +57,9 @@ def load_library(path=None):
     lib = C.CDLL(path)
     vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p
     lib.qoc_abi_version.restype = C.c_int
+    if lib.qoc_abi_version() != QOC_ABI_VERSION:
+        raise QocError("%s has ABI version %d, this package needs %d: rebuild it (python __graft_entry__.py)"
+                       % (path, lib.qoc_abi_version(), QOC_ABI_VERSION))
     lib.qoc_create.argtypes = [C.POINTER(vp), C.POINTER(QocDims)]
     lib.qoc_destroy.argtypes = [vp]
     lib.qoc_last_error.argtypes = [vp]
@@ -149,9 +154,14 @@ class GrapeEngine:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _on_device(self):
+        """Every C call runs with this engine's device current (streams and events belong to it)."""
+        return self.torch.cuda.device(self.device)
+
     def close(self):
         if getattr(self, '_h', None):
-            self.lib.qoc_destroy(self._h)
+            with self._on_device():
+                self.lib.qoc_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -209,8 +219,9 @@ class GrapeEngine:
                        unitary_scale=t.empty(self.B, dtype=t.float64, device=self.device),
                        grad_squared=t.empty(self.B, dtype=t.float64, device=self.device))
         p = lambda x: C.c_void_p(x.data_ptr())
-        self._check(self.lib.qoc_value_and_grad(self._h, p(base), p(out['loss']), p(out['reg_loss']), p(out['grad']),
-                                                p(out['unitary_scale']), p(out['grad_squared']), self._stream()))
+        with self._on_device():
+            self._check(self.lib.qoc_value_and_grad(self._h, p(base), p(out['loss']), p(out['reg_loss']), p(out['grad']),
+                                                    p(out['unitary_scale']), p(out['grad_squared']), self._stream()))
         return out
 
     def evolve(self, base, want_inter_vecs=True):
@@ -222,7 +233,8 @@ class GrapeEngine:
         loss = t.empty(self.B, dtype=t.float64, device=self.device)
         us = t.empty(self.B, dtype=t.float64, device=self.device)
         p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
-        self._check(self.lib.qoc_evolve(self._h, p(base), p(U), p(iv), p(loss), p(us), self._stream()))
+        with self._on_device():
+            self._check(self.lib.qoc_evolve(self._h, p(base), p(U), p(iv), p(loss), p(us), self._stream()))
         return dict(U_final=U, inter_vecs=iv, loss=loss, unitary_scale=us)
 
     # host-buffer entry points (the reference-facing call: run_session.get_error semantics) -----
@@ -273,14 +285,23 @@ class GrapeEngine:
 
     def poll_error(self):
         """Synchronise and raise if a device-side pipeline flagged a failure (tcgen05 path)."""
-        self._check(self.lib.qoc_poll_error(self._h, self._stream()))
+        with self._on_device():
+            self._check(self.lib.qoc_poll_error(self._h, self._stream()))
 
     def propagators(self):
         """Debug view of the cached propagators of the last call as complex128 [B,T,n,n] (clone)."""
         t = self.torch
+        if self.batch_chunk < self.B:
+            raise QocError("propagators(): the batch is processed in chunks of %d < B = %d, the cache only holds the "
+                           "last chunk" % (self.batch_chunk, self.B))
         ptr, eb = C.c_void_p(), C.c_int()
         self._check(self.lib.qoc_debug_propagators(self._h, C.byref(ptr), C.byref(eb)))
         off = ptr.value - self._ws.data_ptr()
+        if self.dims.dtype == QOC_F16X2:        # [B][T][4][n][ld] fp16 planes, value = (h0 + h1) / 2^13
+            ld = (self.n + 15) // 16 * 16
+            nel = self.B * self.T * 4 * self.n * ld
+            raw = self._ws[off:off + nel * 2].view(t.float16).reshape(self.B, self.T, 4, self.n, ld)[..., :self.n].double()
+            return t.complex(raw[:, :, 0] + raw[:, :, 1], raw[:, :, 2] + raw[:, :, 3]) / 8192.0
         if self.dims.dtype == QOC_F64:
             nel = self.B * self.T * self.n * self.n
             return self._ws[off:off + nel * 16].view(t.complex128).reshape(self.B, self.T, self.n, self.n).clone()
@@ -290,12 +311,14 @@ class GrapeEngine:
     KERNELS = ("expm", "chain", "fwd_reduce", "costate", "grad", "finalize")
 
     def set_profiling(self, enable=True):
-        self._check(self.lib.qoc_set_profiling(self._h, int(bool(enable))))
+        with self._on_device():
+            self._check(self.lib.qoc_set_profiling(self._h, int(bool(enable))))
 
     def kernel_times_ms(self):
         """Per-kernel CUDA-event durations (ms) of the last value_and_grad; synchronises."""
         buf = (C.c_float * len(self.KERNELS))()
-        self._check(self.lib.qoc_kernel_times_ms(self._h, buf))
+        with self._on_device():
+            self._check(self.lib.qoc_kernel_times_ms(self._h, buf))
         return dict(zip(self.KERNELS, [float(x) for x in buf]))
 
     @property
