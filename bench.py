@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default: the config's)")
     ap.add_argument("--steps-T", type=int, default=None, help="override the number of time steps (debug only)")
-    ap.add_argument("--dtype", default="f64", choices=["f64", "tf32x3"], help="arithmetic of the propagator stage")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "tf32x3", "f16x2"], help="arithmetic of the propagator stage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -285,7 +285,8 @@ def run_ours(args):
     peak, peak_src = None, None
     if rank == 0:
         tf32 = args.dtype == "tf32x3"
-        N, tdt = (8192, torch.float32) if tf32 else (4096, torch.float64)
+        f16 = args.dtype == "f16x2"
+        N, tdt = (8192, torch.float32) if tf32 else (8192, torch.float16) if f16 else (4096, torch.float64)
         old_flag = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
         a = torch.randn(N, N, device=dev, dtype=tdt)
@@ -300,7 +301,7 @@ def run_ours(args):
         torch.backends.cuda.matmul.allow_tf32 = old_flag
         peak = 2 * N ** 3 / best / 1e9
         peak_src = ("cuBLAS %s %d^3 via torch.matmul, best of 5, measured in this run (MEASURED_PEAKS.json has no %s entry)"
-                    % ("TF32 GEMM" if tf32 else "DGEMM", N, "tf32" if tf32 else "fp64"))
+                    % ("TF32 GEMM" if tf32 else "FP16 GEMM" if f16 else "DGEMM", N, "tf32" if tf32 else "fp16" if f16 else "fp64"))
         del a, bb
     ktimes = {k: v * args.steps / max(sampled, 1) for k, v in ktimes.items()}      # scale the sampled sums to all steps
     expm_ms = ktimes['expm'] / args.steps

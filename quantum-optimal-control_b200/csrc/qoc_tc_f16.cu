@@ -7,17 +7,20 @@
 // the segment chain of one instance).  Matrices live in global memory (L2-resident scratch or the
 // propagator cache in HBM) as split fp16 plane sets (qoc_tc_f16.cuh); a product D = A B is
 //     Dr = Ar Br - Ai Bi,  Di = Ar Bi + Ai Br,   each real product = 3 MMAs (h0 h0 + h0 h1 + h1 h0),
-// i.e. 12 tcgen05.mma.kind::f16 (M = 128, N = n16, K = 16) per 16 columns of K, accumulated in fp32 in
-// TMEM (Dr in columns [0,N), Di in [N,2N)); the sign of the Ai Bi term is the descriptor's negate-A bit.
+// i.e. 12 tcgen05.mma.kind::f16 (M = 128, N <= 128, K = 16) per 16 columns of K, accumulated in fp32 in TMEM; the sign of
+// the Ai Bi term is the descriptor's negate-A bit.  An output is cut into 128-row x (<=128)-column tiles ("quadrants");
+// products with more than one tile (n > 128) alternate between two TMEM accumulator buffers so that the epilogue of a
+// tile overlaps the MMAs of the next one, and completion is tracked per quadrant so that the first tile of the NEXT
+// product starts as soon as the quadrants it reads are written.
 //
-// Roles (320 threads):
-//   warp 0     TMA producer: per 32-wide k-block, four A-plane boxes {32 k x 128 rows} (K-major, SWIZZLE_64B)
-//              and 4 x NG B-plane boxes {64 n x 32 k} (MN-major, SWIZZLE_128B: B is read in its row-major
-//              storage, no transposed copy exists anywhere) into a ring of stages; out-of-range rows /
-//              columns are zero-filled by the 3-D tensor maps (dims {n, n, planes}).
+// Roles (192 threads):
+//   warp 0     TMA producer: per 32-wide k-block, one A box {32 k x 128 rows x 4 planes} (K-major, SWIZZLE_64B) and one
+//              B box {64 n x 32 k x 4 planes} per 64-column group (MN-major, SWIZZLE_128B: B is read in its row-major
+//              storage, no transposed copy exists anywhere) into a ring of stages; out-of-range rows / columns are
+//              zero-filled by the rank-4 tensor maps (dims {n, n, 4 planes, matrices}).
 //   warp 1     MMA issuer: waits full[s], issues 24 MMAs per stage, tcgen05.commit -> empty[s]; after the
-//              last k-block commit -> tmem_full.
-//   warps 2-9  epilogue (two per TMEM lane quarter, even / odd 16-column chunks): tcgen05.ld the accumulator rows (thread = row), apply  c0 D + c1 X + c2 I,
+//              last k-block commit -> tmem_full[buffer].
+//   warps 2-5  epilogue (one per TMEM lane quarter): tcgen05.ld the accumulator rows (thread = row), apply  c0 D + c1 X + c2 I,
 //              re-split into h0/h1 and store the plane set(s) of the result straight to global memory
 //              (each thread writes whole 32-byte sectors of its row); fence.proxy.async + arrive on op_done
 //              so the producer may fetch the result as an operand of the next product.
@@ -34,7 +37,9 @@ namespace {
 constexpr int KB_ELEMS = 32;                     // K elements per stage
 constexpr uint32_t A_PLANE_BYTES = 128 * 64;     // box {32 halfs, 128 rows}
 constexpr uint32_t B_GROUP_BYTES = 32 * 128;     // box {64 halfs, 32 rows}
-constexpr int NEPI = 256;                        // epilogue threads (8 warps: two per TMEM lane quarter)
+constexpr int NEPI = 128;                        // epilogue threads (one warp per TMEM lane quarter; 192 threads leave 255 registers)
+constexpr int NHALF = NEPI / 128;                // epilogue warps per lane quarter (they interleave 16-column chunks)
+constexpr int CSTEP = 16 * NHALF;
 constexpr int NTHREADS = 64 + NEPI;
 constexpr int MAX_STAGES = 4;
 constexpr long long TIMEOUT_CYCLES = 4000000000LL;
@@ -73,6 +78,12 @@ DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, in
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 DEVINL void mma_f16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -96,7 +107,7 @@ DEVINL uint32_t elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(e));
   return e;
 }
-DEVINL void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+DEVINL void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
 
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor layout): start >> 4 | LBO >> 4 << 16 |
 // SBO >> 4 << 32 | version 1 << 46 | layout type << 61 (SWIZZLE_128B = 2, SWIZZLE_64B = 4)
@@ -206,6 +217,14 @@ DEVINL void store_planes16(__half* mat, size_t plane, int ld, int row, int col, 
   stg256(p0 + 2 * plane, b0);
   stg256(p0 + 3 * plane, b1);
 }
+// one component (Re or Im): planes pl0 (h0) and pl0 + 1 (h1)
+DEVINL void store_comp16(__half* p0, size_t plane, const float (&v)[16]) {
+  uint32_t a0[8], a1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], a0[i], a1[i]);
+  stg256(p0, a0);
+  stg256(p0 + plane, a1);
+}
 DEVINL void unpack16(const uint32_t (&h0)[8], const uint32_t (&h1)[8], float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -215,35 +234,34 @@ DEVINL void unpack16(const uint32_t (&h0)[8], const uint32_t (&h1)[8], float (&v
   }
 }
 
+// which 128-row block of an operand a k-block of B rows lives in
+DEVINL int rb_of_kb(int kb) { return (kb * KB_ELEMS) >> 7; }
+
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull, bar_tempty, bar_opdone;
+  __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2], bar_done[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int dead_s;
   __shared__ float wts[32];
+  __shared__ double rs[2][128][2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = q.n, ld = q.ld, N16 = q.N16, NP32 = q.NP32, NG = q.NG, RB = q.RB, KBLK = q.KBLK, NS = q.stages;
-  const uint32_t b_plane_bytes = (uint32_t)NG * B_GROUP_BYTES;
+  const int n = q.n, ld = q.ld, N16 = q.N16, NT0 = q.NT0, NH = q.NH, NGT = q.NGT, DIOFF = q.DIOFF, NBUF = q.NBUF, RB = q.RB,
+            KBLK = q.KBLK, NS = q.stages;
+  const int NQ = RB * NH;                                             // tiles (output quadrants) per product
+  const uint32_t b_plane_bytes = (uint32_t)NGT * B_GROUP_BYTES;
   const uint32_t stage_bytes = 4 * A_PLANE_BYTES + 4 * b_plane_bytes;
   const size_t plane = (size_t)n * ld, mat = 4 * plane;
-  unsigned char* jtile = smem + (size_t)NS * stage_bytes;            // [32 k][64 n] fp16, MN-major SWIZZLE_128B: jval on the diagonal
   long long t_wait0 = 0, t_wait1 = 0, t_work = 0;                    // per-role cycle counters (q.prof)
+  const bool expm = q.prog == TC_PROG_EXPM;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    mbar_init(&bar_tfull, 1);
-    mbar_init(&bar_tempty, NEPI);
-    mbar_init(&bar_opdone, NEPI);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], NEPI); }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_done[i], NEPI);
     dead_s = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 32 * 64; i += NTHREADS) {                    // J[k][nn] = jval * delta(k, nn)
-    const int k = i >> 6, nn = i & 63;
-    const uint32_t off = (uint32_t)(k * 128 + ((((nn >> 3) ^ (k & 7))) << 4) + (nn & 7) * 2);
-    *reinterpret_cast<__half*>(jtile + off) = __float2half(nn == k ? q.jval : 0.0f);
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)q.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -255,119 +273,123 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
   volatile int* dead = &dead_s;
   const bool prof = q.prof != nullptr;
 
+  // Completion phases of the per-quadrant barriers bar_done[rb * NH + nh], counted per CTA: every item contributes one
+  // phase for its prologue (EXPM only) and one per product.  Product j of an item may read a quadrant of its scratch
+  // operands once phase  base + [EXPM] + j  of that quadrant's barrier has completed.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t it = 0, done_cnt = 0;               // stage-use counter, op_done phase counter
-      for (long long item = blockIdx.x; item < q.items && !*dead; item += gridDim.x) {
+      uint32_t it = 0;                             // ring fill counter
+      uint32_t seen[4] = {0, 0, 0, 0};             // phases of bar_done[i] consumed so far
+      uint32_t base_ph = 0;                        // phases completed by earlier items
+      bool ok = true;
+      auto need = [&](int i, uint32_t target) {    // block until bar_done[i] has completed `target` phases
+        if (seen[i] >= target) return;
+        while (ok && seen[i] < target) {
+          const long long c0 = prof ? clock64() : 0;
+          ok = mbar_wait(&bar_done[i], seen[i] & 1, dead);
+          ++seen[i];
+          if (prof) t_wait0 += clock64() - c0;
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");       // the epilogue's generic-proxy stores before our async-proxy loads
+      };
+      for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
         const int nops = item_nops(q, item);
-        for (int j = 0; j < nops && !*dead; ++j) {
+        const uint32_t pro = expm ? 1u : 0u;
+        for (int j = 0; j < nops && ok; ++j) {
           OpR o; make_op(q, item, j, nops, o);
-          // scratch operands (and X built by the prologue) must be complete: one op_done phase per product, plus one
-          // per item prologue (EXPM).  Operands from other classes were written by an earlier kernel.
-          const bool need = (q.prog == TC_PROG_EXPM) || j > 0;
-          if (need) {
-            const long long c0 = prof ? clock64() : 0;
-            if (!mbar_wait(&bar_opdone, done_cnt & 1, dead)) break;
-            ++done_cnt;
-            if (prof) t_wait0 += clock64() - c0;
-          }
-          asm volatile("fence.proxy.async;" ::: "memory");
+          const uint32_t tgt = base_ph + pro + (uint32_t)j;          // phases that must be complete before reading scratch
+          const bool dep = expm || j > 0;
           const CUtensorMap* ma = &maps.a[o.a_cls];
           const CUtensorMap* mb = &maps.b[o.b_cls];
-          const int za = (int)(o.a_idx * 4), zb = (int)(o.b_idx * 4);
-          for (int rb = 0; rb < RB && !*dead; ++rb) {
-            for (int kb = 0; kb < KBLK; ++kb, ++it) {
-              const int s = it % NS;
-              const long long c0 = prof ? clock64() : 0;
-              if (!mbar_wait(&bar_empty[s], ((it / NS) & 1) ^ 1, dead)) break;
-              if (prof) t_wait1 += clock64() - c0;
-              mbar_expect_tx(&bar_full[s], stage_bytes);
-              const uint32_t sa = smem_u32(smem) + s * stage_bytes, sbb = sa + 4 * A_PLANE_BYTES;
-#pragma unroll
-              for (int pl = 0; pl < 4; ++pl) tma_load_3d(sa + pl * A_PLANE_BYTES, ma, kb * KB_ELEMS, rb * 128, za + pl, &bar_full[s]);
-              for (int pl = 0; pl < 4; ++pl)
-                for (int g = 0; g < NG; ++g)
-                  tma_load_3d(sbb + pl * b_plane_bytes + g * B_GROUP_BYTES, mb, g * 64, kb * KB_ELEMS, zb + pl, &bar_full[s]);
-            }
-          }
+          const int za = (int)o.a_idx, zb = (int)o.b_idx;
+          for (int rb = 0; rb < RB && ok; ++rb)
+            for (int nh = 0; nh < NH && ok; ++nh)
+              for (int kb = 0; kb < KBLK && ok; ++kb, ++it) {
+                if (dep) {
+                  need(rb * NH + ((NH == 2 && kb * KB_ELEMS >= NT0) ? 1 : 0), tgt);      // A: rows rb, columns of k-block kb
+                  need((RB == 2 ? rb_of_kb(kb) : 0) * NH + nh, tgt);                     // B: rows of k-block kb, columns of half nh
+                }
+                const int s = it % NS;
+                const long long c0 = prof ? clock64() : 0;
+                ok = ok && mbar_wait(&bar_empty[s], ((it / NS) & 1) ^ 1, dead);
+                if (prof) t_wait1 += clock64() - c0;
+                if (!ok) break;
+                mbar_expect_tx(&bar_full[s], stage_bytes);
+                const uint32_t sa = smem_u32(smem) + s * stage_bytes, sbb = sa + 4 * A_PLANE_BYTES;
+                // one instruction per box: all four planes of the A tile, all four planes of each 64-column group of the B tile
+                tma_load_4d(sa, ma, kb * KB_ELEMS, rb * 128, 0, za, &bar_full[s]);
+                for (int g = 0; g < NGT; ++g)
+                  tma_load_4d(sbb + g * 4 * B_GROUP_BYTES, mb, nh * NT0 + g * 64, kb * KB_ELEMS, 0, zb, &bar_full[s]);
+              }
         }
-        {   // consume the op_done phase of the item's last product
-          if (*dead || !mbar_wait(&bar_opdone, done_cnt & 1, dead)) break;
-          ++done_cnt;
-        }
+        base_ph += pro + (uint32_t)nops;
+        for (int i = 0; i < NQ; ++i) need(i, base_ph);   // catch up with the item's last phases (keeps the parity bookkeeping exact)
       }
       if (prof) { q.prof[(size_t)blockIdx.x * 8 + 0] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 1] = t_wait1; }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(N16 >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A/B f16, A K-major, B MN-major
-    const uint32_t idesc_na = idesc | (1u << 13);                                                          // negate A
-    const uint32_t idesc_j = (1u << 4) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);            // N = 32 (J tile)
+    const uint32_t idesc0 = (1u << 4) | (1u << 16) | ((128u >> 4) << 24);          // D f32, A/B f16, A K-major, B MN-major, M = 128
     const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
-    const uint32_t sj = sbase + NS * stage_bytes;
-    uint32_t it = 0, acc_cnt = 0;
+    uint32_t it = 0, ti = 0;                       // ring fill counter, tile counter (accumulator buffer = ti % NBUF)
     bool ok = true;
     for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
       const int nops = item_nops(q, item);
-      for (int j = 0; j < nops && ok; ++j) {
-        const bool usej = q.prog == TC_PROG_EXPM && q.ops[j].usej;
-        for (int rb = 0; rb < RB && ok; ++rb, ++acc_cnt) {
-          long long c0 = prof ? clock64() : 0;
-          ok = __all_sync(0xffffffffu, mbar_wait(&bar_tempty, (acc_cnt & 1) ^ 1, dead));   // accumulators drained by the epilogue
-          if (!ok) break;
-          if (prof) t_wait0 += clock64() - c0;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kb = 0; kb < KBLK && ok; ++kb, ++it) {
-            const int s = it % NS;
-            c0 = prof ? clock64() : 0;
-            ok = __all_sync(0xffffffffu, mbar_wait(&bar_full[s], (it / NS) & 1, dead));
+      for (int j = 0; j < nops && ok; ++j)
+        for (int rb = 0; rb < RB && ok; ++rb)
+          for (int nh = 0; nh < NH && ok; ++nh, ++ti) {
+            const int nt = nh == 0 ? NT0 : N16 - NT0;                              // columns of this tile
+            const uint32_t idesc = idesc0 | ((uint32_t)(nt >> 3) << 17);
+            const uint32_t idesc_na = idesc | (1u << 13);                          // negate A
+            const int buf = (int)(ti % NBUF);
+            const uint32_t use = ti / NBUF;
+            long long c0 = prof ? clock64() : 0;
+            ok = __all_sync(0xffffffffu, mbar_wait(&bar_tempty[buf], (use & 1) ^ 1, dead));   // accumulator drained by the epilogue
             if (!ok) break;
-            if (prof) t_wait1 += clock64() - c0;
+            if (prof) t_wait0 += clock64() - c0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-              const uint32_t sa = sbase + s * stage_bytes, sbb = sa + 4 * A_PLANE_BYTES;
+            const uint32_t dr = tbase + (uint32_t)(buf * 2 * DIOFF), di = dr + (uint32_t)DIOFF;
+            for (int kb = 0; kb < KBLK && ok; ++kb, ++it) {
+              const int s = it % NS;
+              c0 = prof ? clock64() : 0;
+              ok = __all_sync(0xffffffffu, mbar_wait(&bar_full[s], (it / NS) & 1, dead));
+              if (!ok) break;
+              if (prof) t_wait1 += clock64() - c0;
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              if (elect_one()) {
+                const uint32_t sa = sbase + s * stage_bytes, sbb = sa + 4 * A_PLANE_BYTES;
 #pragma unroll
-              for (int k16 = 0; k16 < 2; ++k16) {
-                uint64_t da[4], db[4];
+                for (int k16 = 0; k16 < 2; ++k16) {
+                  uint64_t da[4], db[4];
 #pragma unroll
-                for (int pl = 0; pl < 4; ++pl) {
-                  da[pl] = make_desc(sa + pl * A_PLANE_BYTES + k16 * 32, q.a_lbo, q.a_sbo, 4);
-                  db[pl] = make_desc(sbb + pl * b_plane_bytes + k16 * 2048, q.b_lbo, q.b_sbo, 2);
+                  for (int pl = 0; pl < 4; ++pl) {
+                    da[pl] = make_desc(sa + pl * A_PLANE_BYTES + k16 * 32, q.a_lbo, q.a_sbo, 4);
+                    db[pl] = make_desc(sbb + pl * B_GROUP_BYTES + k16 * 2048, q.b_lbo, q.b_sbo, 2);
+                  }
+                  const uint32_t first = (kb == 0 && k16 == 0) ? 0u : 1u;
+                  // planes: 0 = Re h0, 1 = Re h1, 2 = Im h0, 3 = Im h1
+                  mma_f16_ss(dr, da[0], db[1], idesc, first);             // Ar0 Br1
+                  mma_f16_ss(dr, da[1], db[0], idesc, 1u);                // Ar1 Br0
+                  mma_f16_ss(dr, da[2], db[3], idesc_na, 1u);             // -Ai0 Bi1
+                  mma_f16_ss(dr, da[3], db[2], idesc_na, 1u);             // -Ai1 Bi0
+                  mma_f16_ss(dr, da[0], db[0], idesc, 1u);                // Ar0 Br0
+                  mma_f16_ss(dr, da[2], db[2], idesc_na, 1u);             // -Ai0 Bi0
+                  mma_f16_ss(di, da[0], db[3], idesc, first);             // Ar0 Bi1
+                  mma_f16_ss(di, da[1], db[2], idesc, 1u);                // Ar1 Bi0
+                  mma_f16_ss(di, da[2], db[1], idesc, 1u);                // Ai0 Br1
+                  mma_f16_ss(di, da[3], db[0], idesc, 1u);                // Ai1 Br0
+                  mma_f16_ss(di, da[0], db[2], idesc, 1u);                // Ar0 Bi0
+                  mma_f16_ss(di, da[2], db[0], idesc, 1u);                // Ai0 Br0
                 }
-                const uint32_t first = (kb == 0 && k16 == 0) ? 0u : 1u;
-                const uint32_t dr = tbase, di = tbase + (uint32_t)NP32;
-                // planes: 0 = Re h0, 1 = Re h1, 2 = Im h0, 3 = Im h1
-                mma_f16_ss(dr, da[0], db[1], idesc, first);             // Ar0 Br1
-                mma_f16_ss(dr, da[1], db[0], idesc, 1u);                // Ar1 Br0
-                mma_f16_ss(dr, da[2], db[3], idesc_na, 1u);             // -Ai0 Bi1
-                mma_f16_ss(dr, da[3], db[2], idesc_na, 1u);             // -Ai1 Bi0
-                mma_f16_ss(dr, da[0], db[0], idesc, 1u);                // Ar0 Br0
-                mma_f16_ss(dr, da[2], db[2], idesc_na, 1u);             // -Ai0 Bi0
-                mma_f16_ss(di, da[0], db[3], idesc, first);             // Ar0 Bi1
-                mma_f16_ss(di, da[1], db[2], idesc, 1u);                // Ar1 Bi0
-                mma_f16_ss(di, da[2], db[1], idesc, 1u);                // Ai0 Br1
-                mma_f16_ss(di, da[3], db[0], idesc, 1u);                // Ai1 Br0
-                mma_f16_ss(di, da[0], db[2], idesc, 1u);                // Ar0 Bi0
-                mma_f16_ss(di, da[2], db[0], idesc, 1u);                // Ai0 Br0
-                if (usej) {                                             // D[:, 32 kb + c] += jval * A[:, 32 kb + c]
-                  const uint64_t dj = make_desc(sj + k16 * 2048, q.b_lbo, q.b_sbo, 2);
-                  const uint32_t cj = (uint32_t)(kb * 32);
-                  mma_f16_ss(dr + cj, da[1], dj, idesc_j, 1u);
-                  mma_f16_ss(dr + cj, da[0], dj, idesc_j, 1u);
-                  mma_f16_ss(di + cj, da[3], dj, idesc_j, 1u);
-                  mma_f16_ss(di + cj, da[2], dj, idesc_j, 1u);
-                }
+                umma_commit(&bar_empty[s]);
+                if (kb == KBLK - 1) umma_commit(&bar_tfull[buf]);
               }
-              umma_commit(&bar_empty[s]);
-              if (kb == KBLK - 1) umma_commit(&bar_tfull);
+              __syncwarp();
             }
-            __syncwarp();
           }
-        }
-      }
     }
     if (prof && lane == 0) { q.prof[(size_t)blockIdx.x * 8 + 2] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 3] = t_wait1; }
   } else {
@@ -376,12 +398,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
     const int half = (warp - 2) >> 2;              // which of the two warps of this lane quarter: even / odd 16-column chunks
     const int et = (warp - 2) * 32 + lane;
     const int lrow = qd * 32 + lane;
-    const uint32_t lane_addr = taddr + ((uint32_t)(qd * 32) << 16);
-    uint32_t acc_cnt = 0;
+    uint32_t ti = 0;
     bool ok = true;
     for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
       const int nops = item_nops(q, item);
-      if (q.prog == TC_PROG_EXPM) {
+      if (expm) {
         // X' = xscale (A_0 + sum_k u_k A_k), u_k = maxA_k sin(base[b][k][t])  (init_tf_ops_weight, :168-185)
         const long long b = item / q.T;
         const int t = (int)(item % q.T);
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
           store_planes16(X, plane, ld, r, c16, re, im);
         }
         asm volatile("fence.proxy.async;" ::: "memory");
-        mbar_arrive(&bar_opdone);
+        for (int i = 0; i < NQ; ++i) mbar_arrive(&bar_done[i]);
         epi_bar();                                   // X is read back (elementwise source) by other threads than its writers
       } else if (q.prog == TC_PROG_CHAIN) {
         if (et == 0) q.scal[(size_t)item * 8 + 5] = 0.0;
@@ -419,95 +440,104 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
         __half* D1 = o.d1_cls >= 0 ? q.base[o.d1_cls] + (size_t)o.d1_idx * mat : nullptr;
         __half* D2 = o.d2_cls >= 0 ? q.base[o.d2_cls] + (size_t)o.d2_idx * mat : nullptr;
         const bool useE = E && (o.c1[1] != 0.f || o.c2[1] != 0.f);
-        for (int rb = 0; rb < RB && ok; ++rb, ++acc_cnt) {
-          const int row = rb * 128 + lrow;
-          const bool vrow = row < n;
-          // elementwise source of the first chunk, fetched while the MMAs still run
-          uint32_t eraw[4][8];
-          const bool ldE = useE && vrow;
-          auto fetchE = [&](int c0) {
-            if (ldE) {
-              const __half* p0 = E + (size_t)row * ld + c0;
+        double sr = 0.0, si = 0.0;                   // row sums of the final product (unitary_scale), over both column halves
+        for (int rb = 0; rb < RB && ok; ++rb)
+          for (int nh = 0; nh < NH && ok; ++nh, ++ti) {
+            const int nt = nh == 0 ? NT0 : N16 - NT0, cbase = nh * NT0;
+            const int buf = (int)(ti % NBUF);
+            const uint32_t use = ti / NBUF;
+            const uint32_t lane_addr = taddr + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * 2 * DIOFF);
+            const int row = rb * 128 + lrow;
+            const bool vrow = row < n;
+            if (nh == 0) { sr = 0.0; si = 0.0; }
+            // elementwise source (b_j X of a Horner step, 2 E of a squaring): two chunks in flight, the first two fetched
+            // while the MMAs of this tile still run
+            uint32_t e0[4][8], e1[4][8];
+            const bool ldE = useE && vrow;
+            auto fetchE = [&](int c0, uint32_t (&e)[4][8]) {
+              if (ldE && c0 < nt) {
+                const __half* p0 = E + (size_t)row * ld + cbase + c0;
 #pragma unroll
-              for (int pl = 0; pl < 4; ++pl) ldg256(p0 + pl * plane, eraw[pl]);
-            }
-          };
-          fetchE(16 * half);
-          long long c0t = prof ? clock64() : 0;
-          ok = __all_sync(0xffffffffu, mbar_wait(&bar_tfull, acc_cnt & 1, dead));
-          if (!ok) break;
-          if (prof) { const long long c1t = clock64(); t_wait0 += c1t - c0t; c0t = c1t; }
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          double sr = 0.0, si = 0.0;                 // row sum of the final product (unitary_scale)
-          for (int c0 = 16 * half; c0 < N16; c0 += 32) {
-            uint32_t ur[16], ui[16];
-            tmem_ld16(lane_addr + (uint32_t)c0, ur);
-            tmem_ld16(lane_addr + (uint32_t)(NP32 + c0), ui);
-            float er[16], ei[16];
-            if (useE) { unpack16(eraw[0], eraw[1], er); unpack16(eraw[2], eraw[3], ei); }
-            else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) er[i] = ei[i] = 0.f;
-            }
-            if (c0 + 32 < N16) fetchE(c0 + 32);      // next chunk's source in flight behind this chunk's arithmetic
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (!vrow) continue;
-            float dr[16], di[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { dr[i] = __uint_as_float(ur[i]); di[i] = __uint_as_float(ui[i]); }
-            if (D1) {
-              float orr[16], oi[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                orr[i] = fmaf(o.c1[0], dr[i], o.c1[1] * er[i]) + ((c0 + i == row) ? o.c1[2] : 0.f);
-                oi[i] = fmaf(o.c1[0], di[i], o.c1[1] * ei[i]);
+                for (int pl = 0; pl < 4; ++pl) ldg256(p0 + pl * plane, e[pl]);
               }
-              store_planes16(D1, plane, ld, row, c0, orr, oi);
-            }
-            if (D2) {
-              float orr[16], oi[16];
+            };
+            fetchE(16 * half, e0);
+            fetchE(16 * half + CSTEP, e1);
+            long long c0t = prof ? clock64() : 0;
+            ok = __all_sync(0xffffffffu, mbar_wait(&bar_tfull[buf], use & 1, dead));
+            if (!ok) break;
+            if (prof) { const long long c1t = clock64(); t_wait0 += c1t - c0t; c0t = c1t; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // one 16-column chunk: accumulator rows out of TMEM, elementwise term from `e`, split, store; `e` is refilled
+            // for the chunk two ahead
+            auto chunk = [&](int c0, uint32_t (&e)[4][8]) {
+              uint32_t ur[16], ui[16];
+              tmem_ld16(lane_addr + (uint32_t)c0, ur);
+              tmem_ld16(lane_addr + (uint32_t)(DIOFF + c0), ui);
+              float er[16], ei[16];
+              if (useE) { unpack16(e[0], e[1], er); unpack16(e[2], e[3], ei); fetchE(c0 + 2 * CSTEP, e); }
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              if (!vrow) return;
+              const int col = cbase + c0;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                orr[i] = fmaf(o.c2[0], dr[i], o.c2[1] * er[i]) + ((c0 + i == row) ? o.c2[2] : 0.f);
-                oi[i] = fmaf(o.c2[0], di[i], o.c2[1] * ei[i]);
-              }
-              store_planes16(D2, plane, ld, row, c0, orr, oi);
-            }
-            if (o.f64out) {
-              const double sc = 1.0 / ((double)(1 << TC_EU) * (double)(1 << TC_EU));
-              double2* U = q.Ufin + (size_t)item * n * n + (size_t)row * n;
+              for (int comp = 0; comp < 2; ++comp) {      // Re: planes 0,1; Im: planes 2,3
+                float ov[16];
+                if (D1) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + i < n) {
-                  const double xr = (double)dr[i] * sc, xi = (double)di[i] * sc;
-                  U[c0 + i] = make_double2(xr, xi);
-                  sr += xr; si += xi;
+                  for (int i = 0; i < 16; ++i) {
+                    const float d = __uint_as_float(comp == 0 ? ur[i] : ui[i]);
+                    const float ee = useE ? (comp == 0 ? er[i] : ei[i]) : 0.f;
+                    ov[i] = fmaf(o.c1[0], d, o.c1[1] * ee) + ((comp == 0 && col + i == row) ? o.c1[2] : 0.f);
+                  }
+                  store_comp16(D1 + (size_t)(2 * comp) * plane + (size_t)row * ld + col, plane, ov);
                 }
-            }
-          }
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&bar_tempty);
-          if (o.f64out) {
-            // unitary_scale = (1/n) sum_r |sum_c X_rc|^2  (init_tf_propagator, tensorflow_state.py:225 on the real embedding);
-            // the two warps of a lane quarter hold the even / odd column chunks of the same rows
-            __shared__ double rs[2][128][2];
-            rs[half][lrow][0] = sr; rs[half][lrow][1] = si;
-            epi_bar();
-            if (half == 0) {
-              const double tr = rs[0][lrow][0] + rs[1][lrow][0], ti = rs[0][lrow][1] + rs[1][lrow][1];
-              double v = vrow ? (tr * tr + ti * ti) / (double)n : 0.0;
+                if (D2) {
 #pragma unroll
-              for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-              if (lane == 0) atomicAdd(&q.scal[(size_t)item * 8 + 5], v);
+                  for (int i = 0; i < 16; ++i) {
+                    const float d = __uint_as_float(comp == 0 ? ur[i] : ui[i]);
+                    const float ee = useE ? (comp == 0 ? er[i] : ei[i]) : 0.f;
+                    ov[i] = fmaf(o.c2[0], d, o.c2[1] * ee) + ((comp == 0 && col + i == row) ? o.c2[2] : 0.f);
+                  }
+                  store_comp16(D2 + (size_t)(2 * comp) * plane + (size_t)row * ld + col, plane, ov);
+                }
+              }
+              if (o.f64out) {
+                const double sc = 1.0 / ((double)(1 << TC_EU) * (double)(1 << TC_EU));
+                double2* U = q.Ufin + (size_t)item * n * n + (size_t)row * n;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (col + i < n) {
+                    const double xr = (double)__uint_as_float(ur[i]) * sc, xi = (double)__uint_as_float(ui[i]) * sc;
+                    U[col + i] = make_double2(xr, xi);
+                    sr += xr; si += xi;
+                  }
+              }
+            };
+            for (int c0 = 16 * half; c0 < nt; c0 += 2 * CSTEP) {
+              chunk(c0, e0);
+              if (c0 + CSTEP < nt) chunk(c0 + CSTEP, e1);
             }
-            epi_bar();
-          }
-          if (rb == RB - 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&bar_tempty[buf]);
+            if (o.f64out && nh == NH - 1) {
+              // unitary_scale = (1/n) sum_r |sum_c X_rc|^2  (init_tf_propagator, tensorflow_state.py:225 on the real embedding);
+              // the two warps of a lane quarter hold the even / odd column chunks of the same rows
+              rs[half][lrow][0] = sr; rs[half][lrow][1] = si;
+              if (NHALF == 1) { rs[1][lrow][0] = 0.0; rs[1][lrow][1] = 0.0; }
+              epi_bar();
+              if (half == 0) {
+                const double tr = rs[0][lrow][0] + rs[1][lrow][0], tq = rs[0][lrow][1] + rs[1][lrow][1];
+                double v = vrow ? (tr * tr + tq * tq) / (double)n : 0.0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) atomicAdd(&q.scal[(size_t)item * 8 + 5], v);
+              }
+              epi_bar();
+            }
             asm volatile("fence.proxy.async;" ::: "memory");
-            mbar_arrive(&bar_opdone);
+            mbar_arrive(&bar_done[rb * NH + nh]);      // this quadrant of the product's outputs is complete
+            if (prof) t_work += clock64() - c0t;
           }
-          if (prof) t_work += clock64() - c0t;
-        }
       }
     }
     if (prof && et == 0) { q.prof[(size_t)blockIdx.x * 8 + 4] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 5] = t_work; }
@@ -528,21 +558,24 @@ bool tc_geometry(int n, TcGeom* g) {
   g->n = n;
   g->ld = tc_ld(n);
   g->N16 = (n + 15) / 16 * 16;
-  g->NP32 = (n + 31) / 32 * 32;
-  g->NG = (g->N16 + 63) / 64;
+  g->NH = g->N16 > 128 ? 2 : 1;
+  g->NT0 = g->NH == 2 ? 128 : g->N16;
+  g->NGT = (g->NT0 + 63) / 64;
+  g->DIOFF = (g->NT0 + 31) / 32 * 32;
   g->RB = n > 128 ? 2 : 1;
+  g->NBUF = g->RB * g->NH > 1 ? 2 : 1;
   g->KBLK = (n + KB_ELEMS - 1) / KB_ELEMS;
   int cols = 32;
-  while (cols < 2 * g->NP32) cols *= 2;
+  while (cols < g->NBUF * 2 * g->DIOFF) cols *= 2;
   g->tmem_cols = cols;
-  const size_t stage = 4 * (size_t)A_PLANE_BYTES + 4 * (size_t)g->NG * B_GROUP_BYTES;
+  const size_t stage = 4 * (size_t)A_PLANE_BYTES + 4 * (size_t)g->NGT * B_GROUP_BYTES;
   const size_t budget = 225 * 1024;
-  g->ctas_per_sm = (n <= 64) ? 2 : 1;
-  int st = (int)((budget / g->ctas_per_sm - 2048 - 4096) / stage);
+  g->ctas_per_sm = 1;
+  int st = (int)((budget - 2048) / stage);
   if (st > MAX_STAGES) st = MAX_STAGES;
   if (st < 1) return false;
   g->stages = st;
-  g->smem = (size_t)st * stage + 4096 + 1024;
+  g->smem = (size_t)st * stage + 1024;
   g->mat_halfs = (size_t)4 * n * g->ld;
   return true;
 }
@@ -561,11 +594,12 @@ const char* tc_make_map(CUtensorMap* map, const void* base, int n, int ld, unsig
       return "cuTensorMapEncodeTiled is not available from the driver";
     fn = (PFN_encodeTiled)p;
   }
-  const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)(4ull * n_mats)};
-  const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)n * ld * 2};
-  const cuuint32_t box_a[3] = {KB_ELEMS, 128, 1}, box_b[3] = {64, KB_ELEMS, 1};
-  const cuuint32_t es[3] = {1, 1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, b_form ? box_b : box_a, es,
+  // rank 4: {column, row, plane, matrix}; a box spans the four planes, so one TMA instruction moves a whole operand tile
+  const cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)n, 4, (cuuint64_t)n_mats};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)n * ld * 2, (cuuint64_t)4 * n * ld * 2};
+  const cuuint32_t box_a[4] = {KB_ELEMS, 128, 4, 1}, box_b[4] = {64, KB_ELEMS, 4, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, b_form ? box_b : box_a, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, b_form ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -635,11 +669,11 @@ void tc_build_expm_ops(int p, int s, int eX, int eY, std::vector<TcExpmOp>& ops)
     ops.push_back(o);
     cur ^= 1;
   }
-  for (int i = 0; i < s; ++i) {                           // E <- 2 E + E E   (+ I after the last one)
+  for (int i = 0; i < s; ++i) {                           // E <- E E + 2 E   (+ I after the last one)
     clear(o);
-    o.sa = o.sb = o.se = (int8_t)cur;                     // 2E is added by the epilogue in fp32 round-to-nearest (riding it on
-    o.d1 = (int8_t)(cur ^ 1);                             // the MMA stream through the J tile -- usej -- costs a decade of accuracy:
-    o.c1[0] = (float)ldexp(1.0, -TC_EU);                  // the accumulator then holds |2E| during every truncating accumulation)
+    o.sa = o.sb = o.se = (int8_t)cur;                     // 2 E is added by the epilogue in fp32 round-to-nearest: riding it on the
+    o.d1 = (int8_t)(cur ^ 1);                             // MMA stream (B = E + 2I, or a diagonal tile) costs a decade of accuracy --
+    o.c1[0] = (float)ldexp(1.0, -TC_EU);                  // the accumulator would hold |2E| during the truncating accumulations
     o.c1[1] = 2.0f;
     o.c1[2] = (i == s - 1) ? (float)sU : 0.0f;
     ops.push_back(o);
@@ -667,10 +701,9 @@ void tc_pack_host(const double* z, int n, int ld, int e, __half* out) {
 
 cudaError_t tc_launch(const TcParams& q_in, const TcMaps& maps, const TcGeom& g, int grid, cudaStream_t st) {
   TcParams q = q_in;
-  q.n = g.n; q.ld = g.ld; q.N16 = g.N16; q.NP32 = g.NP32; q.NG = g.NG; q.RB = g.RB; q.KBLK = g.KBLK; q.stages = g.stages; q.tmem_cols = g.tmem_cols;
+  q.n = g.n; q.ld = g.ld; q.N16 = g.N16; q.NT0 = g.NT0; q.NH = g.NH; q.NGT = g.NGT; q.DIOFF = g.DIOFF; q.NBUF = g.NBUF; q.RB = g.RB; q.KBLK = g.KBLK; q.stages = g.stages; q.tmem_cols = g.tmem_cols;
   if (!q.a_sbo) { q.a_lbo = 1; q.a_sbo = 512 >> 4; }                    // K-major SWIZZLE_64B: 8-row groups 512 B apart
-  if (!q.b_sbo) { q.b_lbo = B_GROUP_BYTES >> 4; q.b_sbo = 1024 >> 4; }  // MN-major SWIZZLE_128B: n-groups 4096 B, k-atoms 1024 B
-  if (q.jval == 0.f) q.jval = (float)(1 << (TC_EU + 1));
+  if (!q.b_sbo) { q.b_lbo = (4 * B_GROUP_BYTES) >> 4; q.b_sbo = 1024 >> 4; }  // MN-major SWIZZLE_128B: 64-column groups 16 KB apart ([group][plane] tiles), k-atoms 1024 B
   cudaError_t e = cudaFuncSetAttribute(k_tc_prog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
   if (grid < 1) grid = 1;

@@ -33,18 +33,17 @@ enum { TC_PROG_EXPM = 0, TC_PROG_SEG = 1, TC_PROG_CHAIN = 2, TC_PROG_GEMM = 3 };
 struct TcExpmOp {
   int8_t sa, sb, d1, d2;         // scratch slots; d1/d2 = -1: none, TC_SLOT_OUT: P[b][t]
   int8_t se;                     // slot of the elementwise source "X" of c[1]
-  int8_t usej;                   // D += jval * slot[sa] through the diagonal J tile (the 2E term of a squaring in E form)
   float c1[3], c2[3];
 };
 
 struct TcMaps {                  // TMA descriptors per buffer class
-  CUtensorMap a[TC_NCLS];        // A form: box {32 k, 128 rows, 1}, SWIZZLE_64B  (K-major operand tiles)
-  CUtensorMap b[TC_NCLS];        // B form: box {64 n, 32 k, 1},     SWIZZLE_128B (MN-major operand tiles)
+  CUtensorMap a[TC_NCLS];        // A form: box {32 k, 128 rows, 4 planes, 1}, SWIZZLE_64B  (K-major operand tiles)
+  CUtensorMap b[TC_NCLS];        // B form: box {64 n, 32 k, 4 planes, 1},     SWIZZLE_128B (MN-major operand tiles)
 };
 
 struct TcParams {
   int prog;
-  int n, ld, N16, NP32, NG, RB, KBLK, stages, tmem_cols;
+  int n, ld, N16, NT0, NH, NGT, DIOFF, NBUF, RB, KBLK, stages, tmem_cols;
   long long items;
   __half* base[TC_NCLS];         // plane-set arrays; matrix i of a class at base + i * 4 n ld
   // EXPM
@@ -54,13 +53,15 @@ struct TcParams {
   int L, S, chain_cls, chain_len;
   double2* Ufin; double* scal;
   int* err_flag;
-  float jval;                    // value on the diagonal of the J tile (fp16-representable)
   unsigned long long* prof;      // optional [grid][8] cycle counters (tools/tc_prog_test.cu)
   // shared-memory matrix descriptor fields (>> 4), overridable by the probe tool
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
 };
 
-struct TcGeom { int n, ld, N16, NP32, NG, RB, KBLK, stages, tmem_cols, ctas_per_sm; size_t smem, mat_halfs; };
+// N16 = n rounded up to 16 (MMA N granularity at M = 128).  Output tiles are 128 rows x NT columns with NT = N16 when
+// N16 <= 128, else two column halves [0,128) and [128,N16) (aligned to the 64-column TMA boxes); NGT = 64-column groups
+// per half.  Accumulator buffer: Dr at +0, Di at +DIOFF, NBUF buffers (two when a product has more than one tile).
+struct TcGeom { int n, ld, N16, NT0, NH, NGT, DIOFF, NBUF, RB, KBLK, stages, tmem_cols, ctas_per_sm; size_t smem, mat_halfs; };
 static __host__ __device__ inline int tc_ld(int n) { return (n + 15) / 16 * 16; }
 
 // host helpers (qoc_tc_f16.cu)
