@@ -2,6 +2,7 @@
 write golden fixtures to tests/golden/ -- TEST INFRASTRUCTURE, never imported by the product.
 
     python oracle/run_reference.py            # regenerates tests/golden/ref_*.npz
+    python oracle/run_reference.py r2 [name]  # regenerates tests/golden/ref2_*.npz (round-2 cases)
 
 The reference is Python-2.7 / TensorFlow-1 source.  Nothing is copied or edited on disk: each
 module is read from /root/reference at import time, passed through the purely syntactic py2->py3
@@ -13,7 +14,8 @@ reference's own.
 
 Syntactic fixes applied in memory: tabs->8 spaces; ``print x`` statements -> ``print(x)``;
 ``xrange`` -> ``range``; the three implicit relative imports -> absolute; ``len(a)/len(b)`` ->
-``//`` inside np.reshape shapes (run_session.py:153,185).
+``//`` inside np.reshape shapes (run_session.py:153,185); the 2-D ``x0`` handed to ``scipy.optimize.minimize``
+(run_session.py:180) is flattened, which the SciPy of the reference's era did itself.
 
 This script needs /root/reference and therefore only runs in the build container; the fixtures it
 writes are committed and are what travels to the GPU box.
@@ -65,6 +67,9 @@ def py2_to_py3(src):
                       "from %s.core.regularization_functions import get_reg_loss" % PKG)
     src = src.replace("len(x)/len(self.sys_para.ops_c)", "len(x)//len(self.sys_para.ops_c)")
     src = src.replace("len(res['x'])/len(self.sys_para.ops_c)", "len(res['x'])//len(self.sys_para.ops_c)")
+    # the SciPy of the reference's era flattened a 2-D x0 itself (lbfgsb.py: x0 = asarray(x0).ravel()); today's raises
+    head, sep, tail = src.partition("def bfgs_optimize")
+    src = head + sep + tail.replace("x0 = self.sys_para.ops_weight_base\n", "x0 = np.reshape(self.sys_para.ops_weight_base, -1)\n", 1)
     return src
 
 
@@ -168,9 +173,22 @@ def run_reference_case(problem, guess, convergence, method='Adam', dtype='float3
                        eval_inter_vecs_packed=captured['inter_vecs'], eval_final_state=captured['final_state'],
                        exp_terms=captured['exp_terms'], scaling=captured['scaling'])
         tf1_shim.reset()
-        uks, Uf = Grape(*args, convergence=convergence, initial_guess=guess, method=method, save=False,
-                        show_plots=False, use_gpu=False, **kw)
-    out.update(uks=np.array(uks), U_final=np.array(Uf))
+        import quantum_optimal_control.core.run_session as rs2
+        fin = {}
+        orig2 = rs2.run_session.get_end_results
+
+        def spy2(self):
+            fin['iterations'], fin['loss'] = int(self.iterations), float(self.l)
+            return orig2(self)
+
+        rs2.run_session.get_end_results = spy2
+        try:
+            uks, Uf = Grape(*args, convergence=convergence, initial_guess=guess, method=method, save=False,
+                            show_plots=False, use_gpu=False, **kw)
+        finally:
+            rs2.run_session.get_end_results = orig2
+    out.update(uks=np.array(uks), U_final=np.array(Uf), run_iterations=fin.get('iterations', -1),
+               run_final_loss=fin.get('loss', np.nan))
     return out
 
 
@@ -193,8 +211,67 @@ def golden_cases():
     }
 
 
+def golden_cases_r2():
+    """Round-2 fixtures: name -> dict(pb, seeds, conv, method).  Early stop with mixed stop times, the SciPy driver,
+    dressed basis + forbid_dressed, U0 != I, and the sizes the fp32-class tcgen05 path (dtype 'f16x2') is checked at
+    (n = 36 is ``c3_small_forbidden`` above; n = 64 and n = 216 here, two seeds each)."""
+    import workloads as W
+    sys.path.insert(0, os.path.join(ROOT, "quantum-optimal-control_b200"))
+    conv = lambda it, tgt=1e-12, rate=0.01: {'rate': rate, 'update_step': 10, 'max_iterations': it, 'conv_target': tgt,
+                                              'learning_rate_decay': 100}
+    # dressed basis of a perturbed C2 drift (helper_functions/grape_functions.py:194-209 semantics, computed by NumPy)
+    c2d = dict(W.c2_transmon_cavity(T=12), total_time=24.0)
+    H0d = c2d['H0'] + 0.05 * (c2d['Hops'][0] + c2d['Hops'][2])
+    from quantum_optimal_control.helper_functions.grape_functions import get_dressed_info      # our NumPy helper
+    w_c, v_c, ids = get_dressed_info(H0d)
+    c2d['H0'] = H0d
+    c2d['dressed_info'] = {'eigenvectors': v_c, 'dressed_id': ids, 'eigenvalues': w_c, 'is_dressed': True}
+    c2d['reg_coeffs'] = {'forbidden_coeff_list': [2.0, 1.0], 'states_forbidden_list': [20, 11], 'forbid_dressed': True}
+    rng5, rng6 = np.random.default_rng(5), np.random.default_rng(6)
+    U0 = np.linalg.qr(rng5.normal(size=(5, 5)) + 1j * rng6.normal(size=(5, 5)))[0]
+    n5 = dict(W.c5_random(5, T=15), U0=U0, states_concerned_list=[1, 3])
+    c64 = dict(W.c5_random(64, T=10), states_concerned_list=[0, 3, 17, 63])
+    c4 = dict(W.c4_three_transmon_toffoli(T=50), total_time=2.5)
+    return {
+        'c1_earlystop': dict(pb=W.c1_pi_pulse(), seeds=[21, 22, 24], conv=conv(40, 0.3, 0.012), method='Adam'),
+        'c1_lbfgs': dict(pb=W.c1_pi_pulse(), seeds=[31], conv=conv(12), method='L-BFGS-B'),
+        'c2_dressed_forbid': dict(pb=c2d, seeds=[41], conv=conv(5), method='Adam'),
+        'n5_U0': dict(pb=n5, seeds=[51], conv=conv(6), method='Adam'),
+        'c5_n64_m4': dict(pb=c64, seeds=[61, 62], conv=conv(3), method='Adam'),
+        'c4_T50': dict(pb=c4, seeds=[71, 72], conv=conv(2), method='Adam'),
+    }
+
+
+def write_r2(names=None):
+    import workloads as W
+    outdir = os.path.join(ROOT, "tests", "golden")
+    for name, c in golden_cases_r2().items():
+        if names and name not in names:
+            continue
+        pb = c['pb']
+        K, T = len(pb['Hops']), pb['steps']
+        for dtype in ('float64', 'float32'):
+            rows = []
+            for seed in c['seeds']:
+                guess = W.random_guess(K, T, pb['maxA'], seed)
+                res = run_reference_case(pb, guess, c['conv'], method=c['method'], dtype=dtype)
+                res['guess'] = guess
+                rows.append(res)
+            keys = [k for k in rows[0] if k not in ('exp_terms', 'scaling')]
+            data = {k: np.stack([np.asarray(r[k]) for r in rows]) for k in keys}
+            path = os.path.join(outdir, "ref2_%s_%s.npz" % (name, dtype))
+            np.savez_compressed(path, seeds=np.array(c['seeds']), exp_terms=rows[0]['exp_terms'], scaling=rows[0]['scaling'],
+                                max_iterations=c['conv']['max_iterations'], **data)
+            print("%-20s %-8s (p,s)=(%d,%d) its=%s loss0=%s -> %s" % (
+                name, dtype, rows[0]['exp_terms'], rows[0]['scaling'], [int(r['run_iterations']) for r in rows],
+                ["%.5g" % r['eval_loss'] for r in rows], os.path.relpath(path, ROOT)), flush=True)
+
+
 def main():
     import workloads as W
+    if len(sys.argv) > 1 and sys.argv[1] == 'r2':
+        write_r2(sys.argv[2:] or None)
+        return
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
     for name, (pb, seed, conv) in golden_cases().items():

@@ -13,7 +13,7 @@ CONVERGENCE_DEFAULTS = {
 
 class Convergence:
     """Holds the convergence settings (attribute names as in core/convergence.py:16-58) and the
-    recorded history; plotting lives in ``core/reporting.py`` and is optional."""
+    recorded history (the reference's matplotlib summary, core/convergence.py:121-222, is out of scope)."""
 
     def __init__(self, sys_para, time_unit, convergence):
         self.sys_para = sys_para

@@ -76,9 +76,10 @@ class run_session:
     """Same constructor shape and result attributes (``uks``, ``Uf``) as the reference class."""
 
     def __init__(self, engine, conv, sys_para, method, show_plots=True, single_simulation=False, use_gpu=True,
-                 quiet=False, run_file=None):
+                 quiet=False, run_file=None, return_dtype=None):
         import torch
         self.torch = torch
+        self.return_dtype = return_dtype
         self.engine = engine
         self.conv = conv
         self.sys_para = sys_para
@@ -214,6 +215,10 @@ class run_session:
         Uf = ev['U_final'].cpu().numpy()
         self.inter_vecs = None if ev['inter_vecs'] is None else ev['inter_vecs'].cpu().numpy()
         self.engine.poll_error()
+        if getattr(self, 'return_dtype', None) == 'reference':
+            # the reference returns float32 pulses (run_session.py:112-117, float32 session) and a complex64 final
+            # state (analysis.py:18-24 on a float32 fetch)
+            uks, Uf = uks.astype(np.float32), Uf.astype(np.complex64)
         if sp.batched:
             self.uks, self.Uf = uks, Uf
         else:
@@ -232,6 +237,9 @@ class run_session:
 
     def minimize_opt_fun(self, x):
         K = self.sys_para.ops_len
+        # the reference assigns ops_weight_base inside get_error (run_session.py:121): the per-iteration records
+        # (uks, final_state, inter_vecs) written by update_and_save must describe the CURRENT iterate
+        self.base.copy_(self.torch.from_numpy(np.ascontiguousarray(np.reshape(x, (1, K, len(x) // K)), dtype=np.float64)))
         l, rl, grads, metric, g2 = self.get_error(np.reshape(x, (K, len(x) // K)))
         self.l, self.rl, self.g_squared, self.metric = (np.array([v]) for v in (l, rl, g2, metric))
         if l < self.conv.conv_target:

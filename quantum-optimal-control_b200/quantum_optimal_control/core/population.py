@@ -63,6 +63,9 @@ def grape_population(grape_fn, args, initial_guesses, group=None, **kwargs):
     total = len(initial_guesses)
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if total < world:
+        # an empty shard cannot build an engine (B = 0) and the other ranks would wait in the all-gather forever
+        raise ValueError("population of %d instances on %d ranks: every rank needs at least one instance" % (total, world))
     lo, hi = shard_bounds(total, rank, world)
     uks, Uf, losses = grape_fn(*args, initial_guess=np.asarray(initial_guesses)[lo:hi], return_losses=True, **kwargs)
     dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')

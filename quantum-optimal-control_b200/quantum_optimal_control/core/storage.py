@@ -27,12 +27,18 @@ except Exception:                           # noqa: BLE001
 
 
 def new_run_file(data_path, file_name):
-    """NNNNN_<name>.h5 with the first free 5-digit prefix (main_grape/grape.py:44-50)."""
+    """NNNNN_<name>.h5 with the first free 5-digit prefix (main_grape/grape.py:44-50).  The name is RESERVED
+    atomically (the empty file is created with O_CREAT | O_EXCL) so that concurrent processes -- one per GPU in
+    ``core.population`` -- never resolve the same path."""
     ext = ".h5" if h5py is not None else ".npz"
     num = 0
-    while os.path.exists(os.path.join(data_path, str(num).zfill(5) + "_" + file_name + ext)):
-        num += 1
-    return os.path.join(data_path, str(num).zfill(5) + "_" + file_name + ext)
+    while True:
+        path = os.path.join(data_path, str(num).zfill(5) + "_" + file_name + ext)
+        try:
+            os.close(os.open(path, os.O_CREAT | os.O_EXCL | os.O_WRONLY))
+            return path
+        except FileExistsError:
+            num += 1
 
 
 class RunFile:
@@ -41,7 +47,10 @@ class RunFile:
     def __init__(self, path):
         self.path = path
         self._once, self._series = {}, {}
-        if h5py is None and os.path.exists(path):
+        if os.path.exists(path) and os.path.getsize(path) == 0:        # name reserved by new_run_file, nothing written yet
+            if h5py is not None:
+                os.remove(path)
+        elif h5py is None and os.path.exists(path):
             with np.load(path, allow_pickle=True) as f:
                 self._once = {k: f[k] for k in f.files}
 

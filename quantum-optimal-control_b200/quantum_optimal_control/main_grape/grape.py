@@ -2,7 +2,9 @@
 signature and return value ``(uks, U_final)``, running on the B200 engine.
 
 Additive keywords (ours): ``batch`` (number of independent random initialisations when no
-``initial_guess`` is given), ``dtype`` ('f64'), ``device``, ``quiet``; ``initial_guess`` may be
+``initial_guess`` is given), ``dtype`` ('f64' | 'f16x2' | 'tf32x3': arithmetic of the propagator stage),
+``return_dtype`` (None: float64 / complex128 results; 'reference': float32 ``uks`` and complex64 ``U_final`` as the
+reference returns them, core/run_session.py:112-117, core/analysis.py:18-24), ``device``, ``quiet``; ``initial_guess`` may be
 [B, K, T], in which case ``uks`` is [B, K, T] and ``U_final`` is [B, n, n]; ``return_losses=True`` appends the
 per-instance final losses (used by ``core.population`` for multi-GPU sweeps).
 """
@@ -23,10 +25,12 @@ def Grape(H0, Hops, Hnames, U, total_time, steps, states_concerned_list, converg
           sparse_K=False, draw=None, initial_guess=None, show_plots=True, unitary_error=1e-4, method='Adam',
           state_transfer=False, no_scaling=False, freq_unit='GHz', file_name=None, save=True, data_path=None,
           Taylor_terms=None, use_inter_vecs=True, batch=None, dtype='f64', device=None, quiet=False,
-          return_losses=False):
+          return_losses=False, return_dtype=None):
     grape_start_time = time.time()
     time_unit = {"GHz": "ns", "MHz": "us", "KHz": "ms", "Hz": "s"}[freq_unit]       # grape.py:25-26
 
+    if return_dtype not in (None, 'reference'):
+        raise ValueError("return_dtype must be None or 'reference'")
     if not use_gpu:
         raise NotImplementedError("use_gpu=False: this build has no CPU path; the GRAPE hot path runs on "
                                   "sm_100a (B200) only")
@@ -73,7 +77,7 @@ def Grape(H0, Hops, Hnames, U, total_time, steps, states_concerned_list, converg
     conv = Convergence(sys_para, time_unit, convergence)
     try:
         SS = run_session(engine, conv, sys_para, method, show_plots=sys_para.show_plots, use_gpu=use_gpu, quiet=quiet,
-                         run_file=run_file)
+                         run_file=run_file, return_dtype=return_dtype)
         if save:
             run_file.add('wall_clock_time', np.array(time.time() - grape_start_time))     # grape.py:123-127
             if not quiet:

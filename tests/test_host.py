@@ -96,7 +96,8 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert not missing, missing
     from quantum_optimal_control.core.engine import SYMBOLS, load_library
     assert sorted(SYMBOLS) == declared
-    assert load_library().qoc_abi_version() == 1
+    from quantum_optimal_control.core.engine import QOC_ABI_VERSION
+    assert load_library().qoc_abi_version() == QOC_ABI_VERSION == int(re.search(r"#define QOC_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_no_cpu_fallback(built_lib):

@@ -159,3 +159,35 @@ def test_reference_quirks():
 
 def test_golden_files_present():
     assert len(glob.glob(os.path.join(GOLD, "ref_*_float64.npz"))) == len(golden_cases())
+
+
+# ---- round-2 fixtures (oracle/run_reference.py r2): early stop, dressed + forbid_dressed, U0 != I, n = 64 / 216 ------------
+from oracle.run_reference import golden_cases_r2  # noqa: E402
+
+
+@pytest.mark.parametrize("name", [k for k, c in golden_cases_r2().items() if c['method'] == 'Adam'])
+def test_oracle_matches_r2_reference_goldens_fp64(name):
+    c = golden_cases_r2()[name]
+    g = np.load(os.path.join(GOLD, "ref2_%s_float64.npz" % name))
+    args, kw = W.grape_kwargs(c['pb'])
+    H0, Hops, Hn, U, tt, steps, scl = args
+    for b in range(len(g['seeds'])):
+        setup = O.make_setup(H0, Hops, U, tt, steps, scl, initial_guess=g['guess'][b], **kw)
+        assert (setup.exp_terms, setup.scaling) == (int(g['exp_terms']), int(g['scaling']))
+        out = O.graph_value_and_grad(setup, setup.ops_weight_base)
+        assert abs(out.loss - g['eval_loss'][b]) < 1e-12
+        assert abs(out.reg_loss - g['eval_reg_loss'][b]) < 1e-12 * max(1, abs(g['eval_reg_loss'][b]))
+        assert np.abs(out.grad - g['eval_grad'][b]).max() < 1e-11 * max(1.0, np.abs(g['eval_grad'][b]).max())
+        assert np.abs(out.final_state - g['eval_final_state'][b]).max() < 1e-11
+        if name == 'c4_T50':
+            break                                  # n = 216: one evaluation of one seed keeps the CPU suite short
+        uks, Uf = O.grape(*args, convergence=c['conv'], initial_guess=g['guess'][b], **kw)
+        assert np.abs(uks - g['uks'][b]).max() < 1e-10           # incl. the iterate at which the early stop fired
+        assert np.linalg.norm(Uf - g['U_final'][b]) < 1e-10
+
+
+def test_r2_fixture_early_stop_has_mixed_stop_times():
+    g = np.load(os.path.join(GOLD, "ref2_c1_earlystop_float64.npz"))
+    its = [int(i) for i in g['run_iterations']]
+    assert len(set(its)) > 1 and max(its) < int(g['max_iterations'])
+    assert all(float(l) < 0.3 for l in g['run_final_loss'])     # stopped by loss < conv_target (run_session.py:56-58)
