@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- GRAPE iterations/s on BASELINE.json's config (C2 by default) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C1] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5n8..C5n128] [--dtype f64|f16x2|tf32x3]
+                    [--batch B] [--impl ours|reference] [--no-secondary] [--no-cpu-baseline]
+
+The default line is BASELINE config C2 (configs[1], fp64); at N = 1 it also carries ``config.secondary``: short runs of
+every other BASELINE configuration at its stated size (C3 and C4 on the fp32-class tcgen05 path, the C5 sizes on fp64).
 
 A "step" is one GRAPE optimiser iteration of the whole batch: one fwd+bwd (value_and_grad over all
 T time steps for all B instances) plus the TF1-form Adam update.  ``value`` counts
@@ -51,6 +55,7 @@ def parse():
     ap.add_argument("--steps-T", type=int, default=None, help="override the number of time steps (debug only)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "tf32x3", "f16x2"], help="arithmetic of the propagator stage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of the other BASELINE configs (config.secondary)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -160,20 +165,30 @@ def cpu_reference_rate(pb, steps, warmup, budget_s=None, T_sample=None):
 
 
 def run_reference(args):
+    """Reference arm: the CPU port of the reference graph on ALL host cores.  Two ways of using the cores are timed and the
+    better one is the line's value: (a) one instance, every intra-op thread on its 2n x 2n matmuls (what a single
+    Grape() call does under TensorFlow); (b) one instance per core, each on one thread (sequential Grape() calls spread
+    over the cores) -- for the small matrices of C1-C3 (b) is ~10x higher."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     pb, meta = make_problem(args.workload, args.steps_T)
     n, K, T, m = len(pb['H0']), len(pb['Hops']), pb['steps'], len(pb['states_concerned_list'])
-    rate, cores, done, Ts, per_iter = cpu_reference_rate(pb, args.steps, min(args.warmup, 1), budget_s=240.0)
-    sample = "1 instance x %d reference-style Adam iterations (2 fwd+bwd each, fp32 real-embedded 2n x 2n, T=%d)" % (done, Ts)
+    rate, cores, done, Ts, per_iter = cpu_reference_rate(pb, args.steps, min(args.warmup, 1), budget_s=90.0)
+    sample = "1 instance x %d reference-style Adam iterations (2 fwd+bwd each, fp32 real-embedded 2n x 2n, T=%d), %d intra-op threads" % (done, Ts, cores)
+    extra = cpu_extra_baselines(args.workload, pb, seconds=20.0)
+    pc = extra.get("per_core", {})
+    mode = "intra-op threads"
+    if pc.get("value", 0.0) > rate:
+        rate, per_iter, sample, mode = pc["value"], 1.0 / pc["value"], pc["sample"], "one instance per core"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": min(args.warmup, 1), "ms_per_step": per_iter * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: n=%d K=%d T=%d m=%d, one instance per step (the reference has no batch dim)" % (
-            args.workload, n, K, T, m), "note": "CPU oracle port in reference-cost mode; TF1/py2 reference cannot run here"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "%s: n=%d K=%d T=%d m=%d, one instance per Grape() call (the reference has no batch dim)" % (
+            args.workload, n, K, T, m), "cores_used_as": mode,
+            "note": "CPU oracle port in reference-cost mode; TF1/py2 reference cannot run here"},
+        "cpu_baseline": dict({"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}, **extra),
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -181,7 +196,39 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def measured_peak(torch, dev, dtype):
+    """Tensor-pipe denominator of the roofline: MEASURED_PEAKS.json (driver-written) where it has the entry, else a
+    cuBLAS GEMM timed here.  f64 -> DGEMM, tf32x3 -> TF32 GEMM, f16x2 -> the file's bf16 figure (kind::f16 and bf16 share
+    the tensor pipe rate; sustained figure: the expm kernel runs for >= 0.1 s per launch on the big configs)."""
+    if dtype == "f16x2":
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            return float(mp["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)", float(mp["bf16_tflops"])
+        except Exception:  # noqa: BLE001
+            return 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md; MEASURED_PEAKS.json absent: of fallback)", 1590.0
+    tf32 = dtype == "tf32x3"
+    N, tdt = (8192, torch.float32) if tf32 else (4096, torch.float64)
+    old_flag = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    a = torch.randn(N, N, device=dev, dtype=tdt)
+    bb = torch.randn(N, N, device=dev, dtype=tdt)
+    for _ in range(2):
+        a @ bb
+    best = 1e9
+    for _ in range(5):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); a @ bb; s1.record(); torch.cuda.synchronize()
+        best = min(best, s0.elapsed_time(s1))
+    torch.backends.cuda.matmul.allow_tf32 = old_flag
+    del a, bb
+    src = ("cuBLAS %s %d^3 via torch.matmul, best of 5, measured in this run (MEASURED_PEAKS.json has no %s entry)"
+           % ("TF32 GEMM" if tf32 else "DGEMM", N, "tf32" if tf32 else "fp64"))
+    return 2 * N ** 3 / best / 1e9, src, None
+
+
+def measure(workload, dtype, B, steps, warmup, dev, local, world, rank, steps_T=None, e2e=True, want_peak=True):
+    """One configuration on this rank's GPU: device-resident loop (value), host-buffer loop (e2e), per-stage CUDA events,
+    roofline of the propagator kernel.  Returns a dict (rank-local times; the caller reduces over ranks)."""
     import torch
     import torch.distributed as dist
     import workloads as W
@@ -189,26 +236,18 @@ def run_ours(args):
     from quantum_optimal_control.core.engine import GrapeEngine
     from quantum_optimal_control.core.optimizer import TF1AdamState, TF1AdamHost as HostAdam
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-
-    pb, meta = make_problem(args.workload, args.steps_T)
-    B = args.batch or meta['B']
+    pb, meta = make_problem(workload, steps_T)
+    B = B or meta['B']
     n, K, T, m = len(pb['H0']), len(pb['Hops']), pb['steps'], len(pb['states_concerned_list'])
     guess = W.random_guess(K, T, pb['maxA'], 1000 * rank, B=B)           # each rank: its own B seeds (weak scaling)
     pargs, kw = W.grape_kwargs(pb)
-    H0, Hops, Hn, U, tt, steps, scl = pargs
+    H0, Hops, Hn, U, tt, nsteps, scl = pargs
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
-        sp = SystemParameters(H0, Hops, Hn, U, np.identity(n), tt, steps, scl, None, kw['maxA'], None, guess, False,
+        sp = SystemParameters(H0, Hops, Hn, U, np.identity(n), tt, nsteps, scl, None, kw['maxA'], None, guess, False,
                               kw.get('unitary_error', 1e-4), False, False, kw.get('reg_coeffs'), False, None,
                               kw.get('Taylor_terms'), True, True, False, False, False)
-    eng = GrapeEngine.from_sys_para(sp, device=dev, dtype=args.dtype)
+    eng = GrapeEngine.from_sys_para(sp, device=dev, dtype=dtype)
     p, s = sp.exp_terms, sp.scaling
     base0 = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).to(dev)
 
@@ -228,7 +267,7 @@ def run_ours(args):
         out = eng.value_and_grad(base, out=out)
         adam.step(base, out['grad'], lr)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     eng.set_profiling(True)
     ktimes = {k: 0.0 for k in eng.KERNELS}
@@ -238,9 +277,9 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         e0.record()
         sampled = 0
-        for i in range(args.steps):
+        for i in range(steps):
             step()
-            if i % 8 == 0 or i == args.steps - 1:           # per-kernel events are read (one sync) on a subset of steps
+            if i % 8 == 0 or i == steps - 1:                # per-kernel events are read (one sync) on a subset of steps
                 for k, v in eng.kernel_times_ms().items():
                     ktimes[k] += v
                 sampled += 1
@@ -249,127 +288,244 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
     eng.set_profiling(False)
-    final_loss = float(out['loss'].min().item())
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    ms_per_step = ms_max / args.steps
-    value = B * world * args.steps / (ms_max * 1e-3)
+    eng.poll_error()
+    res = dict(workload=workload, dtype=dtype, B=B, n=n, K=K, T=T, m=m, p=p, s=s, ms=ms, steps=steps, launches=int(launches),
+               clocks=clk.summary(), final_loss=float(out['loss'].min().item()), losses=out['loss'].clone(),
+               batch_chunk=eng.batch_chunk)
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
-    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))      # host Adam: share the cores between ranks
-    hbase = eng.host_buffers()['base']                      # pinned host weights, updated in place by the host Adam
-    hbase[...] = np.asarray(sp.ops_weight_base, dtype=np.float64)
-    hadam = HostAdam(hbase.shape, threads=max(1, min(16 if world == 1 else 4, (os.cpu_count() or 1) // max(world, 1))))
-    for _ in range(max(3, min(args.warmup, 5))):
-        o = eng.value_and_grad_host(hbase, copy=False)
-        hadam.step(hbase, o['grad'], lr)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 50))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        o = eng.value_and_grad_host(hbase, copy=False)      # pinned H2D of the weights, kernels, D2H of grad + losses
-        hadam.step(hbase, o['grad'], lr)
-        _ = float(o['loss'][0])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * e2e_steps / float(t_e.item())
-    h2d = hbase.nbytes
-    d2h = hbase.nbytes + 4 * B * 8
+    if e2e:
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))      # host Adam: share the cores between ranks
+        hbase = eng.host_buffers()['base']                      # pinned host weights, updated in place by the host Adam
+        hbase[...] = np.asarray(sp.ops_weight_base, dtype=np.float64)
+        hadam = HostAdam(hbase.shape, threads=max(1, min(16 if world == 1 else 4, (os.cpu_count() or 1) // max(world, 1))))
+        for _ in range(max(1, min(warmup, 5))):
+            o = eng.value_and_grad_host(hbase, copy=False)
+            hadam.step(hbase, o['grad'], lr)
+        barrier()
+        e2e_steps = max(2, min(steps, 50))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            o = eng.value_and_grad_host(hbase, copy=False)      # pinned H2D of the weights, kernels, D2H of grad + losses
+            hadam.step(hbase, o['grad'], lr)
+            _ = float(o['loss'][0])
+        torch.cuda.synchronize()
+        res.update(e2e_s=time.perf_counter() - t0, e2e_steps=e2e_steps, h2d=int(hbase.nbytes), d2h=int(hbase.nbytes + 4 * B * 8))
 
-    # ---- roofline of the dominant kernel (k_expm) ----------------------------------------------
-    peak, peak_src = None, None
-    if rank == 0:
-        tf32 = args.dtype == "tf32x3"
-        f16 = args.dtype == "f16x2"
-        N, tdt = (8192, torch.float32) if tf32 else (8192, torch.float16) if f16 else (4096, torch.float64)
-        old_flag = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = tf32
-        a = torch.randn(N, N, device=dev, dtype=tdt)
-        bb = torch.randn(N, N, device=dev, dtype=tdt)
-        for _ in range(2):
-            a @ bb
-        best = 1e9
-        for _ in range(5):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(); a @ bb; s1.record(); torch.cuda.synchronize()
-            best = min(best, s0.elapsed_time(s1))
-        torch.backends.cuda.matmul.allow_tf32 = old_flag
-        peak = 2 * N ** 3 / best / 1e9
-        peak_src = ("cuBLAS %s %d^3 via torch.matmul, best of 5, measured in this run (MEASURED_PEAKS.json has no %s entry)"
-                    % ("TF32 GEMM" if tf32 else "FP16 GEMM" if f16 else "DGEMM", N, "tf32" if tf32 else "fp16" if f16 else "fp64"))
-        del a, bb
-    ktimes = {k: v * args.steps / max(sampled, 1) for k, v in ktimes.items()}      # scale the sampled sums to all steps
-    expm_ms = ktimes['expm'] / args.steps
+    # ---- roofline of the dominant kernel (the propagator stage) ----------------------------------
+    ktimes = {k: v * steps / max(sampled, 1) for k, v in ktimes.items()}      # scale the sampled sums to all steps
+    expm_ms = ktimes['expm'] / steps
     expm_flops = 8.0 * n ** 3 * (p - 1 + s) * T * B                    # (p-1) Taylor products + s squarings per (b,t)
     achieved = expm_flops / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else None
     step_flops = flops_alg(n, T, m, K, p, s) * B
     ps_products = (1 + p // 2 - (1 if p % 2 == 0 else 0)) if p >= 2 else 0          # Paterson-Stockmeyer product count
-    np_pad = 32 if args.dtype == "tf32x3" else (n + 7) // 8 * 8
     hermitian = all(np.allclose(h, np.conj(np.transpose(h))) for h in [H0] + list(Hops))
-    if args.dtype == "f64" and hermitian and np_pad in (16, 32) and p >= 2:
-        nblk = np_pad // 8                       # Hermitian-structure path: p//2 + 1 products on the upper block triangle
-        taylor_equiv = (p // 2 + 1) * (nblk * (nblk + 1) / 2.0) / (nblk * nblk)
+    peak = peak_src = peak_burst = None
+    if want_peak and rank == 0:
+        peak, peak_src, peak_burst = measured_peak(torch, dev, dtype)
+    if dtype == "f16x2":
+        n16 = (n + 15) // 16 * 16
+        rows = 128 * (2 if n > 128 else 1)
+        kpad = (n + 31) // 32 * 32
+        nprod = max(1, ps_products) + s                                 # products issued per (b,t)
+        executed = 2.0 * rows * n16 * kpad * 12 * nprod * T * B         # 12 real MMAs (4 real products x 3 half-pairs) per k-step
+        kname = "k_tc_prog<EXPM> (tcgen05 kind::f16, TMA-fed, fp16-pair operands)"
+        pipe = "fp16 tensor pipe via tcgen05 (3 MMAs per real product: h0 h0 + h0 h1 + h1 h0), fp32 accumulators in TMEM"
+        kernels = ("f16x2: expm = k_tc_prog<EXPM>; chain = k_plane_sweep<fwd> (states, fp64) on the handle's high-priority stream "
+                   "while k_tc_prog<SEG> + k_tc_prog<CHAIN> (U_final, unitary_scale) run on the caller's stream; costate = "
+                   "k_plane_sweep<rev>; grad / fwd_reduce / finalize as on the fp64 path")
     else:
-        taylor_equiv = ps_products
-    # fp64: complex products are evaluated with 3 real DMMA products (Gauss / 3M) instead of 4 -> 6 n^3 issued flops
-    executed = (8.0 if args.dtype == "tf32x3" else 6.0) * np_pad ** 3 * (taylor_equiv + s) * T * B * (3 if args.dtype == "tf32x3" else 1)
-    kname = "k_expm_tc32 (tcgen05)" if args.dtype == "tf32x3" else "k_expm_mma (DMMA)"
-    traffic = None                       # dram bytes per launch from the committed ncu capture (same workload only)
+        np_pad = 32 if dtype == "tf32x3" else (n + 7) // 8 * 8
+        if dtype == "f64" and hermitian and np_pad in (16, 32) and p >= 2:
+            nblk = np_pad // 8                   # Hermitian-structure path: p//2 + 1 products on the upper block triangle
+            taylor_equiv = (p // 2 + 1) * (nblk * (nblk + 1) / 2.0) / (nblk * nblk)
+        else:
+            taylor_equiv = ps_products
+        # fp64: complex products are evaluated with 3 real DMMA products (Gauss / 3M) instead of 4 -> 6 n^3 issued flops
+        executed = (8.0 if dtype == "tf32x3" else 6.0) * np_pad ** 3 * (taylor_equiv + s) * T * B * (3 if dtype == "tf32x3" else 1)
+        kname = "k_expm_tc32 (tcgen05)" if dtype == "tf32x3" else ("k_expm_mma (DMMA)" if n <= 64 else "k_expm_large (DMMA, tiled)")
+        pipe = ("tf32 tensor pipe via tcgen05 (3 MMAs per product: 3xTF32 operand split)" if dtype == "tf32x3"
+                else "fp64 (tcgen05 has no f64 kind; bound is the FP64 FMA/DMMA pipe)")
+        kernels = ("f64, few concerned states (m < NP/2): expm = k_expm_mma; chain = k_vec_sweep<fwd> (states, TMA ring) on the "
+                   "handle's high-priority stream while k_segprod + k_chain_mma (U_final, unitary_scale) run on the caller's "
+                   "stream; costate = k_vec_sweep<rev>; finalize includes the join of the two branches")
+    traffic = tr_src = None              # dram bytes per launch from the committed ncu capture of the SAME workload, else null
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kname)
-        if tr and args.workload == "C2" and args.steps_T is None and args.batch is None:
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        trj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        key = "%s/%s" % (workload, dtype)
+        if key in trj and steps_T is None and B == meta['B']:
+            traffic = trj[key]["dram_bytes_read"] + trj[key]["dram_bytes_write"]
+            tr_src = "profiles/r02_traffic.json[%s] (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)" % key
     except Exception:  # noqa: BLE001
         pass
-    roof = {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic,
-            "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
-            "peak_source": peak_src,
-            "pipe": ("tf32 tensor pipe via tcgen05 (3 MMAs per product: 3xTF32 operand split)" if args.dtype == "tf32x3"
-                     else "fp64 (tcgen05 has no f64 kind; bound is the FP64 FMA/DMMA pipe)"),
-            "executed_flops_per_launch": executed,
-            "executed_frac_of_peak": (executed / (expm_ms * 1e-3) / 1e12 / peak) if (expm_ms > 0 and peak) else None,
-            "note": "achieved uses SURVEY 8(d)'s algorithmic count (p-1+s products of 8n^3), so frac can exceed 1: the kernel "
-                    "evaluates the SAME polynomial with fewer products (Paterson-Stockmeyer; for Hermitian Hamiltonians the "
-                    "even/odd split with triangle-only products) and each complex product with 3 real products (3M); "
-                    "executed_* counts the flops actually issued on the padded tile (and the 3x split for tf32x3) and is the "
-                    "hardware-utilisation figure",
-            "kernels": ("f64, few concerned states (m < NP/2): expm = k_expm_mma; chain = k_vec_sweep<fwd> (states, TMA ring) on the "
-                        "handle's high-priority stream while k_segprod + k_chain_mma (U_final, unitary_scale) run on the caller's "
-                        "stream; costate = k_vec_sweep<rev>; finalize includes the join of the two branches"),
-            "alg_flops_per_launch": expm_flops, "avg_launch_ms": expm_ms,
-            "kernel_ms_per_step": {k: v / args.steps for k, v in ktimes.items()},
-            "whole_step_alg_tflops": step_flops / (ms_per_step * 1e-3) / 1e12}
+    res['roofline'] = {
+        "kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic, "traffic_source": tr_src,
+        "peak_source": peak_src, "peak_burst": peak_burst, "pipe": pipe,
+        "executed_flops_per_launch": executed,
+        "executed_frac_of_peak": (executed / (expm_ms * 1e-3) / 1e12 / peak) if (expm_ms > 0 and peak) else None,
+        "note": "achieved uses SURVEY 8(d)'s algorithmic count (p-1+s products of 8n^3 per time step); the kernels evaluate the "
+                "SAME polynomial with fewer products (Paterson-Stockmeyer); executed_* counts the flops actually issued on the "
+                "padded tiles (fp64: 3M products and Hermitian triangle; tf32x3 / f16x2: the 3x operand split) and is the "
+                "hardware-utilisation figure",
+        "kernels": kernels, "alg_flops_per_launch": expm_flops, "avg_launch_ms": expm_ms,
+        "kernel_ms_per_step": {k: v / steps for k, v in ktimes.items()},
+        "whole_step_alg_tflops": step_flops / (ms / steps * 1e-3) / 1e12}
+    res['pb'] = pb
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def _percore_worker(a):
+    """One reference-style iteration stream on ONE thread (the per-core CPU baseline: one instance per core)."""
+    wl, Ts, seconds = a
+    import torch
+    torch.set_num_threads(1)
+    pb, _ = make_problem(wl)
+    import workloads as W
+    from oracle import grape_oracle as O
+    K, T = len(pb['Hops']), pb['steps']
+    pbs = dict(pb, steps=Ts, total_time=pb['total_time'] * Ts / T)
+    args, kw = W.grape_kwargs(pbs)
+    H0, Hops, Hn, U, tt, st, scl = args
+    setup = O.make_setup(H0, Hops, U, tt, st, scl, initial_guess=W.random_guess(K, Ts, pb['maxA'], 0), **kw)
+    base = np.asarray(setup.ops_weight_base, dtype=np.float32)
+    O.graph_value_and_grad(setup, base, torch.float32)
+    t0, it = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        O.graph_value_and_grad(setup, base, torch.float32)
+        O.graph_value_and_grad(setup, base, torch.float32)
+        it += 1
+    return it, time.perf_counter() - t0
+
+
+def cpu_extra_baselines(workload, pb, seconds=8.0):
+    """BASELINE.md section 3: (a) per-core -- one instance per core, each on one thread, all cores busy;
+    (b) generous -- ONE fwd+bwd per iteration in the complex n x n costate form (NumPy complex128, all cores)."""
+    import multiprocessing as mp
+    from oracle import grape_oracle as O
+    import workloads as W
+    cores = os.cpu_count() or 1
+    K, T = len(pb['Hops']), pb['steps']
+    Ts = max(4, min(T, 20))
+    out = {}
+    try:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            rs = pool.map(_percore_worker, [(workload, Ts, seconds)] * cores)
+        rate = sum(it / dt for it, dt in rs) * Ts / T
+        out["per_core"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                           "sample": "%d processes x 1 thread, reference-style iterations (2 fwd+bwd, fp32 real-embedded) at T=%d "
+                                     "for %.0f s, scaled linearly to T=%d" % (cores, Ts, seconds, T)}
+    except Exception as e:  # noqa: BLE001
+        out["per_core"] = {"error": repr(e)[:200]}
+    try:
+        pbs = dict(pb, steps=Ts, total_time=pb['total_time'] * Ts / T)
+        args, kw = W.grape_kwargs(pbs)
+        H0, Hops, Hn, U, tt, st, scl = args
+        setup = O.make_setup(H0, Hops, U, tt, st, scl, initial_guess=W.random_guess(K, Ts, pb['maxA'], 0), **kw)
+        O.costate_value_and_grad(setup, setup.ops_weight_base)
+        t0, it = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds:
+            O.costate_value_and_grad(setup, setup.ops_weight_base)
+            it += 1
+        dt = (time.perf_counter() - t0) / it * (T / Ts)
+        out["generous"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                           "sample": "1 instance, ONE fwd+bwd per iteration, complex128 n x n costate form (NumPy/BLAS, all "
+                                     "cores), T=%d scaled to T=%d; %.3f s per iteration" % (Ts, T, dt)}
+    except Exception as e:  # noqa: BLE001
+        out["generous"] = {"error": repr(e)[:200]}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    r = measure(args.workload, args.dtype, args.batch, args.steps, args.warmup, dev, local, world, rank, steps_T=args.steps_T)
+    B, n, K, T, m, p, s = r['B'], r['n'], r['K'], r['T'], r['m'], r['p'], r['s']
+    t_ms = torch.tensor([r['ms'], r['e2e_s']], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max, e2e_max = float(t_ms[0].item()), float(t_ms[1].item())
+    ms_per_step = ms_max / args.steps
+    value = B * world * args.steps / (ms_max * 1e-3)
+    e2e_value = B * world * r['e2e_steps'] / e2e_max
+
+    # the ONE collective of a population sweep (core/population.py): all-gather of the per-instance losses, verified
+    allgather = None
+    if world > 1:
+        from quantum_optimal_control.core.population import gather_losses
+        allv = gather_losses(r['losses'], B * world)
+        mine = allv[rank * B:(rank + 1) * B]
+        ok = torch.tensor([1.0 if (allv.numel() == B * world and torch.equal(mine, r['losses'])) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        chk = torch.tensor([float(r['losses'].sum().item())], dtype=torch.float64, device=dev)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        allgather = {"backend": dist.get_backend(), "elements": int(allv.numel()), "verified": bool(ok.item() == 1.0) and
+                     abs(float(chk.item()) - float(allv.sum().item())) < 1e-9 * max(1.0, abs(float(chk.item()))),
+                     "best_instance": int(torch.argmin(allv).item())}
+
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary and args.workload == "C2" and args.steps_T is None and args.batch is None:
+        # every other BASELINE configuration at its stated size, short runs (device-resident, CUDA events, clocks sampled)
+        secondary = {}
+        for wl, dt, st, wu in (("C3", "f16x2", 3, 1), ("C3", "f64", 3, 1), ("C4", "f16x2", 2, 1), ("C5n64", "f64", 3, 1),
+                               ("C5n32", "f64", 5, 1), ("C5n16", "f64", 10, 2)):
+            try:
+                q = measure(wl, dt, None, st, wu, dev, local, 1, 0, e2e=False)
+                rf = q['roofline']
+                secondary["%s/%s" % (wl, dt)] = {
+                    "workload": "%s: n=%d K=%d T=%d m=%d B=%d, (p,s)=(%d,%d), %s" % (wl, q['n'], q['K'], q['T'], q['m'], q['B'], q['p'], q['s'], dt),
+                    "ms_per_step": q['ms'] / st, "value": q['B'] * st / (q['ms'] * 1e-3), "unit": UNIT, "steps": st, "warmup": wu,
+                    "batch_chunk": q['batch_chunk'], "clocks": q['clocks'], "gpu_launches": q['launches'],
+                    "roofline": {k: rf[k] for k in ("kernel", "achieved", "peak", "frac", "executed_frac_of_peak", "peak_source",
+                                                    "avg_launch_ms", "kernel_ms_per_step", "whole_step_alg_tflops")}}
+            except Exception as e:  # noqa: BLE001
+                secondary["%s/%s" % (wl, dt)] = {"error": repr(e)[:300]}
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            rate, cores, done, Ts, per_iter = cpu_reference_rate(pb, 50, 1, budget_s=args.cpu_seconds)
+            rate, cores, done, Ts, per_iter = cpu_reference_rate(r['pb'], 50, 1, budget_s=args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "1 instance x %d reference-style Adam iterations (2 fwd+bwd each, fp32 real-embedded, T=%d); "
-                             "%.3f s per iteration" % (done, Ts, per_iter)}
+                   "sample": "1 instance x %d reference-style Adam iterations (2 fwd+bwd each, fp32 real-embedded, T=%d), "
+                             "%d intra-op threads; %.3f s per iteration" % (done, Ts, cores, per_iter)}
+            cpu.update(cpu_extra_baselines(args.workload, r['pb'], seconds=min(8.0, args.cpu_seconds)))
+        dname = {"f64": "f64", "tf32x3": "tf32x3 (fp32 accumulate)", "f16x2": "f16x2 (fp16-pair operands, fp32 accumulate, fp64 states)"}[args.dtype]
+        p_bytes = 16 if args.dtype == "f64" else 8
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if args.dtype == "f64" else "tf32x3 (fp32 accumulate)", "data": "synthetic",
+            "dtype": dname, "data": "synthetic",
             "config": {"workload": "%s: n=%d K=%d T=%d m=%d B=%d per GPU, (p,s)=(%d,%d), %s" % (
                 args.workload, n, K, T, m, B, p, s, args.dtype), "batch_iterations_per_s": args.steps / (ms_max * 1e-3),
                 "l2": "inputs exceed L2: %.2f GB of propagators are rewritten and re-read every step" % (
-                    B * T * n * n * 16 / 1e9), "final_loss_min": final_loss},
-            "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "roofline": roof,
+                    B * T * n * n * p_bytes / 1e9), "final_loss_min": r['final_loss'], "secondary": secondary,
+                "population_allgather": allgather},
+            "clocks": r['clocks'],
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r['h2d'], "d2h_bytes_per_step": r['d2h'],
+                    "steps": r['e2e_steps']},
+            "gpu_launches": r['launches'],
+            "roofline": r['roofline'],
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    eng.close()
+        try:                                         # the peaks measured in this run, next to the other profiles
+            json.dump({"workload": args.workload, "dtype": args.dtype, "peak_tflops": r['roofline']['peak'],
+                       "peak_source": r['roofline']['peak_source'], "n_gpus": world},
+                      open(os.path.join(ROOT, "profiles", "bench_peaks_last_run.json"), "w"), indent=1)
+        except Exception:  # noqa: BLE001
+            pass
     if world > 1:
         dist.destroy_process_group()
 
