@@ -18,6 +18,7 @@ static int pick_np(int n) { return n <= 64 ? (n + 7) / 8 * 8 : -1; }
 struct WsLayout { size_t P, psi, lam, gctrl, ot, scal, Ufin, st_base, st_grad, st_out, seg, scratch, tc_seg, tc_scr, tc_const, total; };
 
 #define QOC_TC_SEG_LEN 16   // propagators per segment product of the QOC_F16X2 U_final branch
+#define QOC_TC_ILV 2        // (b,t) items interleaved per CTA in the propagator program: hides the product-to-product dependency
 
 static int tc_grid_for(const qoc_dims_t& d, int sm_count) {
   TcGeom g;
@@ -53,7 +54,7 @@ static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
   if (tc) {
     off = align_up(off, 1024);
     L.tc_seg = off; off += align_up((size_t)Bc * ((d.T + QOC_TC_SEG_LEN - 1) / QOC_TC_SEG_LEN) * tc_mat, 1024);
-    L.tc_scr = off; off += align_up((size_t)tc_grid_for(d, sm_count) * TC_NSLOT * tc_mat, 1024);
+    L.tc_scr = off; off += align_up((size_t)tc_grid_for(d, sm_count) * QOC_TC_ILV * TC_NSLOT * tc_mat, 1024);
     L.tc_const = off; off += align_up(2 * tc_mat, 1024);
   }
   L.total = off;
@@ -461,7 +462,7 @@ static int tc_prepare(qoc_handle_t h, cudaStream_t st) {
   CUDA_TRY(h, cudaMemcpyAsync(h->tc_const, hbuf.data(), hbuf.size() * sizeof(__half), cudaMemcpyHostToDevice, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
   const void* base[TC_NCLS] = {h->tc_scr, h->P, h->tc_seg, h->tc_const};
-  const unsigned long long cnt[TC_NCLS] = {(unsigned long long)h->tc_grid * TC_NSLOT, (unsigned long long)h->Bc * d.T,
+  const unsigned long long cnt[TC_NCLS] = {(unsigned long long)h->tc_grid * QOC_TC_ILV * TC_NSLOT, (unsigned long long)h->Bc * d.T,
                                            (unsigned long long)h->Bc * h->tc_S, 2ull};
   for (int c = 0; c < TC_NCLS; ++c) {
     const char* e = tc_make_map(&h->tmaps.a[c], base[c], d.n, g.ld, cnt[c], false);
@@ -481,10 +482,13 @@ static void tc_base_params(qoc_handle_t h, TcParams& q) {
 static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   TcParams q;
   tc_base_params(h, q);
-  q.prog = TC_PROG_EXPM; q.items = (long long)p.B * p.T;
+  q.prog = TC_PROG_EXPM; q.items = (long long)p.B * p.T; q.ilv = QOC_TC_ILV;
   q.nops = h->tc_nops; q.ops = h->tc_ops; q.K = p.K; q.T = p.T; q.ctrl = p.base; q.maxA = p.maxA; q.A_f = h->A_f; q.xscale = h->tc_xscale;
   ++h->launches;
-  CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(q.items < h->tc_grid ? q.items : h->tc_grid), st));
+  {
+    const long long rounds = (q.items + QOC_TC_ILV - 1) / QOC_TC_ILV;
+    CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(rounds < h->tc_grid ? rounds : h->tc_grid), st));
+  }
   return QOC_OK;
 }
 

@@ -4,7 +4,7 @@
 //   k_plane_sweep<true> : lambda_j(t) = P_t^dagger lambda_j(t+1) + source_j(t)   (TF autodiff through :214-220)
 //
 // One CTA per instance walks the T steps; a step reads the 8 n ld bytes of P_t exactly once from HBM, in
-// 16-row chunks (4 planes x 16 rows, one cp.async.bulk per plane) through an NST-deep shared-memory ring with
+// R-row chunks (4 planes x R rows, one cp.async.bulk per plane) through an NST-deep shared-memory ring with
 // an mbarrier per stage.  2^13 P = h0 + h1 is exact in fp32 and widened to double; the states stay fp64.
 //   forward: warp = row of the chunk, lane = pair of k (4-byte loads of P, 16-byte loads of the even-k / odd-k halves
 //            of the state vectors: all conflict-free); the 2 m partial sums meet in a shuffle reduce-scatter;
@@ -18,8 +18,6 @@
 
 namespace {
 
-constexpr int R = 16;          // rows per chunk (one per warp in the forward sweep)
-constexpr int NTH = 512;
 
 DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 DEVINL void mbar_init(uint64_t* bar, int count) {
@@ -58,16 +56,28 @@ DEVINL double2 widen2(uint32_t h0, uint32_t h1) {
   return make_double2((double)(fa.x + fb.x), (double)(fa.y + fb.y));
 }
 
-struct PlaneSweepShape { int nst; size_t stage_halfs, smem; };
+// CTA shape: NW warps (4 for n <= 64, 8 for n <= 128, else 16); R rows of P per chunk (a multiple of NW; the whole matrix
+// when it is small, else ~24 KB of planes); NST ring stages within a per-CTA shared-memory budget chosen so that small
+// problems keep several CTAs (instances) resident per SM -- a sweep is a chain of T dependent steps, its latency is hidden
+// by running many instances side by side.
+struct PlaneSweepShape { int nw, R, nst; size_t stage_halfs, smem; };
 
 PlaneSweepShape plane_sweep_shape(int n, int m) {
   PlaneSweepShape s;
   const int ld = tc_ld(n);
-  s.stage_halfs = (size_t)4 * R * ld;
+  s.nw = n <= 64 ? 4 : n <= 128 ? 8 : 16;
+  const size_t stage_target = n <= 64 ? 8 * 1024 : n <= 128 ? 16 * 1024 : 24 * 1024;
+  int r = (int)(stage_target / (8 * (size_t)ld)) / s.nw * s.nw;
+  if (r < s.nw) r = s.nw;
+  const int rfull = (n + s.nw - 1) / s.nw * s.nw;
+  s.R = r < rfull ? r : rfull;
+  s.stage_halfs = (size_t)4 * s.R * ld;
   const size_t vec = (size_t)2 * 8 * ld * sizeof(cplx);          // [2][8][2][ld/2]
   const size_t fixed = vec + 64 + 128;
-  int nst = (int)((220 * 1024 - fixed) / (s.stage_halfs * sizeof(__half)));
+  const size_t budget = n <= 64 ? 36 * 1024 : n <= 128 ? 100 * 1024 : 220 * 1024;
+  int nst = budget > fixed ? (int)((budget - fixed) / (s.stage_halfs * sizeof(__half))) : 0;
   if (nst > 8) nst = 8;
+  if (nst < 2 && fixed + 2 * s.stage_halfs * sizeof(__half) <= 220 * 1024) nst = 2;
   s.nst = nst;
   s.smem = fixed + (size_t)(nst > 0 ? nst : 0) * s.stage_halfs * sizeof(__half);
   (void)m;
@@ -101,8 +111,9 @@ DEVINL double reduce_scatter(double (&a)[NV], int lane, int& idx) {
   return v;
 }
 
-template <bool REV, int MS>
-__global__ void __launch_bounds__(NTH) k_plane_sweep(QocParams p, const __half* __restrict__ Pp, int NST) {
+template <bool REV, int MS, int NW>
+__global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __half* __restrict__ Pp, int NST, int R) {
+  constexpr int NTH = 32 * NW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = p.n, m = p.m, T = p.T, mn = m * n;
   const int ld = tc_ld(n), lh = ld >> 1;
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(NTH) k_plane_sweep(QocParams p, const __half* 
         const uint32_t* St = reinterpret_cast<const uint32_t*>(ring + (size_t)(g % NST) * stage_halfs);
         const size_t pw = (size_t)R * lh;                  // plane stride in 32-bit words
 #pragma unroll 1
-        for (int rr = warp; rr < R; rr += 16) {
+        for (int rr = warp; rr < R; rr += NW) {
           const int row = c * R + rr;
           if (row >= n) break;                             // warp-uniform
           double a[2 * MS];
@@ -242,7 +253,8 @@ __global__ void __launch_bounds__(NTH) k_plane_sweep(QocParams p, const __half* 
       cur ^= 1;
     }
   } else {
-    const int sg = tid >> 7, cp = tid & 127;               // state pair, column pair (columns 2 cp, 2 cp + 1)
+    constexpr int CPN = 8 * NW;                            // column pairs per state pair: 32 / 64 / 128 >= ld / 2
+    const int sg = tid / CPN, cp = tid % CPN;              // state pair, column pair (columns 2 cp, 2 cp + 1)
     const bool act = 2 * sg < m && 2 * cp < ld;
     for (int step = 0; step < nsteps; ++step) {
       const int t = T - 1 - step;
@@ -303,12 +315,20 @@ bool qoc_plane_sweep_supported(int n, int m) {
   return plane_sweep_shape(n, m).nst >= 2;
 }
 
+template <bool REV, int MS, int NW>
+static cudaError_t launch_ps3(const QocParams& p, const void* planes, const PlaneSweepShape& s, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_plane_sweep<REV, MS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_plane_sweep<REV, MS, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  k_plane_sweep<REV, MS, NW><<<p.B, 32 * NW, s.smem, st>>>(p, reinterpret_cast<const __half*>(planes), s.nst, s.R);
+  return cudaGetLastError();
+}
 template <bool REV, int MS>
 static cudaError_t launch_ps(const QocParams& p, const void* planes, const PlaneSweepShape& s, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_plane_sweep<REV, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
-  if (e != cudaSuccess) return e;
-  k_plane_sweep<REV, MS><<<p.B, NTH, s.smem, st>>>(p, reinterpret_cast<const __half*>(planes), s.nst);
-  return cudaGetLastError();
+  if (s.nw == 4) return launch_ps3<REV, MS, 4>(p, planes, s, st);
+  if (s.nw == 8) return launch_ps3<REV, MS, 8>(p, planes, s, st);
+  return launch_ps3<REV, MS, 16>(p, planes, s, st);
 }
 
 cudaError_t qoc_launch_plane_sweep(const QocParams& p, const void* planes, int reverse, cudaStream_t st, int64_t* launches) {

@@ -13,14 +13,14 @@
 // tile overlaps the MMAs of the next one, and completion is tracked per quadrant so that the first tile of the NEXT
 // product starts as soon as the quadrants it reads are written.
 //
-// Roles (192 threads):
+// Roles (320 threads):
 //   warp 0     TMA producer: per 32-wide k-block, one A box {32 k x 128 rows x 4 planes} (K-major, SWIZZLE_64B) and one
 //              B box {64 n x 32 k x 4 planes} per 64-column group (MN-major, SWIZZLE_128B: B is read in its row-major
 //              storage, no transposed copy exists anywhere) into a ring of stages; out-of-range rows / columns are
 //              zero-filled by the rank-4 tensor maps (dims {n, n, 4 planes, matrices}).
 //   warp 1     MMA issuer: waits full[s], issues 24 MMAs per stage, tcgen05.commit -> empty[s]; after the
 //              last k-block commit -> tmem_full[buffer].
-//   warps 2-5  epilogue (one per TMEM lane quarter): tcgen05.ld the accumulator rows (thread = row), apply  c0 D + c1 X + c2 I,
+//   warps 2-9  epilogue (two per TMEM lane quarter, interleaving 16-column chunks): tcgen05.ld the accumulator rows (thread = row), apply  c0 D + c1 X + c2 I,
 //              re-split into h0/h1 and store the plane set(s) of the result straight to global memory
 //              (each thread writes whole 32-byte sectors of its row); fence.proxy.async + arrive on op_done
 //              so the producer may fetch the result as an operand of the next product.
@@ -37,7 +37,7 @@ namespace {
 constexpr int KB_ELEMS = 32;                     // K elements per stage
 constexpr uint32_t A_PLANE_BYTES = 128 * 64;     // box {32 halfs, 128 rows}
 constexpr uint32_t B_GROUP_BYTES = 32 * 128;     // box {64 halfs, 32 rows}
-constexpr int NEPI = 128;                        // epilogue threads (one warp per TMEM lane quarter; 192 threads leave 255 registers)
+constexpr int NEPI = 256;                        // epilogue threads (two warps per TMEM lane quarter)
 constexpr int NHALF = NEPI / 128;                // epilogue warps per lane quarter (they interleave 16-column chunks)
 constexpr int CSTEP = 16 * NHALF;
 constexpr int NTHREADS = 64 + NEPI;
@@ -137,8 +137,9 @@ DEVINL int item_nops(const TcParams& q, long long item) {
   }
 }
 
-DEVINL void make_op(const TcParams& q, long long item, int j, int nops, OpR& o) {
-  const long long sb = (long long)blockIdx.x * TC_NSLOT;
+DEVINL void make_op(const TcParams& q, long long item, int j, int nops, int z, int rpar, OpR& o) {
+  const long long sb = ((long long)blockIdx.x * q.ilv + z) * TC_NSLOT;
+  const int xs = rpar ? 4 : 0;                    // the generator X of odd rounds lives in slot 4 (it is built during the previous round)
   const float cu = 1.0f / (float)(1 << TC_EU);   // unitary x unitary -> unitary scale
   o.e_cls = -1; o.d2_cls = -1; o.d1_cls = -1; o.f64out = 0;
   o.e_idx = o.d1_idx = o.d2_idx = 0;
@@ -147,9 +148,9 @@ DEVINL void make_op(const TcParams& q, long long item, int j, int nops, OpR& o) 
   switch (q.prog) {
     case TC_PROG_EXPM: {
       const TcExpmOp e = q.ops[j];
-      o.a_cls = TC_CLS_SCR; o.a_idx = sb + e.sa;
-      o.b_cls = TC_CLS_SCR; o.b_idx = sb + e.sb;
-      o.e_cls = TC_CLS_SCR; o.e_idx = sb + e.se;
+      o.a_cls = TC_CLS_SCR; o.a_idx = sb + (e.sa == 0 ? xs : e.sa);
+      o.b_cls = TC_CLS_SCR; o.b_idx = sb + (e.sb == 0 ? xs : e.sb);
+      o.e_cls = TC_CLS_SCR; o.e_idx = sb + (e.se == 0 ? xs : e.se);
       if (e.d1 >= 0) {
         if (e.d1 == TC_SLOT_OUT) { o.d1_cls = TC_CLS_P; o.d1_idx = item; } else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + e.d1; }
       }
@@ -240,7 +241,10 @@ DEVINL int rb_of_kb(int kb) { return (kb * KB_ELEMS) >> 7; }
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2], bar_done[4];
+  __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ unsigned int xdone_cnt;               // rounds whose generators X are assembled (EXPM)
+  __shared__ unsigned int done_cnt[4];             // completed phases per output quadrant: monotonic counters (a waiter may lag
+                                                   // several phases behind with two items interleaved: parity barriers would alias)
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int dead_s;
   __shared__ float wts[32];
@@ -254,11 +258,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
   const size_t plane = (size_t)n * ld, mat = 4 * plane;
   long long t_wait0 = 0, t_wait1 = 0, t_work = 0;                    // per-role cycle counters (q.prof)
   const bool expm = q.prog == TC_PROG_EXPM;
+  const int ILV = q.ilv;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], NEPI); }
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_done[i], NEPI);
+    for (int i = 0; i < 4; ++i) done_cnt[i] = 0;
+    xdone_cnt = 0;
     dead_s = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -273,33 +279,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
   volatile int* dead = &dead_s;
   const bool prof = q.prof != nullptr;
 
-  // Completion phases of the per-quadrant barriers bar_done[rb * NH + nh], counted per CTA: every item contributes one
+  // Completion phases of the per-quadrant counters done_cnt[rb * NH + nh], counted per CTA: every round contributes one
   // phase for its prologue (EXPM only) and one per product.  Product j of an item may read a quadrant of its scratch
   // operands once phase  base + [EXPM] + j  of that quadrant's barrier has completed.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;                             // ring fill counter
-      uint32_t seen[4] = {0, 0, 0, 0};             // phases of bar_done[i] consumed so far
-      uint32_t base_ph = 0;                        // phases completed by earlier items
+      uint32_t seen[4] = {0, 0, 0, 0};             // last value of done_cnt[i] observed
+      uint32_t base_ph = 0;                        // phases completed by earlier rounds
       bool ok = true;
-      auto need = [&](int i, uint32_t target) {    // block until bar_done[i] has completed `target` phases
-        if (seen[i] >= target) return;
-        while (ok && seen[i] < target) {
-          const long long c0 = prof ? clock64() : 0;
-          ok = mbar_wait(&bar_done[i], seen[i] & 1, dead);
-          ++seen[i];
-          if (prof) t_wait0 += clock64() - c0;
+      long long t_cat[3] = {0, 0, 0};              // done-waits by cause: prologue, previous product, end of round
+      int cat = 0;
+      uint32_t xseen = 0, round = 0;
+      auto need = [&](int i, uint32_t target) {    // block until quadrant i (i < 4) / the generators (i = 4) reached `target`
+        uint32_t& sn = i < 4 ? seen[i] : xseen;
+        if (sn >= target) return;
+        const long long c0 = clock64();
+        for (;;) {
+          unsigned int v;
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(i < 4 ? &done_cnt[i] : &xdone_cnt)) : "memory");
+          sn = v;
+          if (v >= target) break;
+          if (*dead || clock64() - c0 > TIMEOUT_CYCLES) { *dead = 1; ok = false; break; }
         }
+        if (prof) { const long long dtw = clock64() - c0; t_wait0 += dtw; t_cat[cat] += dtw; }
         asm volatile("fence.proxy.async;" ::: "memory");       // the epilogue's generic-proxy stores before our async-proxy loads
       };
-      for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
-        const int nops = item_nops(q, item);
-        const uint32_t pro = expm ? 1u : 0u;
-        for (int j = 0; j < nops && ok; ++j) {
-          OpR o; make_op(q, item, j, nops, o);
-          const uint32_t tgt = base_ph + pro + (uint32_t)j;          // phases that must be complete before reading scratch
-          const bool dep = expm || j > 0;
+      for (long long it0 = (long long)blockIdx.x * ILV; it0 < q.items && ok; it0 += (long long)gridDim.x * ILV, ++round) {
+        const int nz = (int)min((long long)ILV, q.items - it0);      // items interleaved in this round
+        const int nops = item_nops(q, it0);
+        for (int j = 0; j < nops && ok; ++j)
+         for (int z = 0; z < nz && ok; ++z) {
+          const long long item = it0 + z;
+          OpR o; make_op(q, item, j, nops, z, (int)(round & 1), o);
+          // phases that must be complete before reading scratch: this item's previous product, which sits nz positions
+          // earlier in the stream (and, for the first product, the generators of this round)
+          const uint32_t tgt = base_ph + (j > 0 ? (uint32_t)((j - 1) * nz + z + 1) : 0u);
+          const bool dep = j > 0;
+          cat = j == 0 ? 0 : 1;
+          if (expm && j == 0) need(4, round + 1);
           const CUtensorMap* ma = &maps.a[o.a_cls];
           const CUtensorMap* mb = &maps.b[o.b_cls];
           const int za = (int)o.a_idx, zb = (int)o.b_idx;
@@ -323,10 +342,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
                   tma_load_4d(sbb + g * 4 * B_GROUP_BYTES, mb, nh * NT0 + g * 64, kb * KB_ELEMS, 0, zb, &bar_full[s]);
               }
         }
-        base_ph += pro + (uint32_t)nops;
-        for (int i = 0; i < NQ; ++i) need(i, base_ph);   // catch up with the item's last phases (keeps the parity bookkeeping exact)
+        base_ph += (uint32_t)(nops * nz);
+        cat = 2;
+        for (int i = 0; i < NQ; ++i) need(i, base_ph);   // catch up with the round's last phases (keeps the parity bookkeeping exact)
       }
-      if (prof) { q.prof[(size_t)blockIdx.x * 8 + 0] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 1] = t_wait1; }
+      if (prof) { q.prof[(size_t)blockIdx.x * 8 + 0] = t_wait0; q.prof[(size_t)blockIdx.x * 8 + 1] = t_wait1;
+                  q.prof[(size_t)blockIdx.x * 8 + 6] = t_cat[0]; q.prof[(size_t)blockIdx.x * 8 + 7] = t_cat[1]; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -336,9 +357,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
     const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
     uint32_t it = 0, ti = 0;                       // ring fill counter, tile counter (accumulator buffer = ti % NBUF)
     bool ok = true;
-    for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
-      const int nops = item_nops(q, item);
-      for (int j = 0; j < nops && ok; ++j)
+    for (long long it0 = (long long)blockIdx.x * ILV; it0 < q.items && ok; it0 += (long long)gridDim.x * ILV) {
+      const int nz = (int)min((long long)ILV, q.items - it0);
+      const int nops = item_nops(q, it0);
+      for (int jz = 0; jz < nops * nz && ok; ++jz)
         for (int rb = 0; rb < RB && ok; ++rb)
           for (int nh = 0; nh < NH && ok; ++nh, ++ti) {
             const int nt = nh == 0 ? NT0 : N16 - NT0;                              // columns of this tile
@@ -398,44 +420,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
     const int half = (warp - 2) >> 2;              // which of the two warps of this lane quarter: even / odd 16-column chunks
     const int et = (warp - 2) * 32 + lane;
     const int lrow = qd * 32 + lane;
-    uint32_t ti = 0;
+    uint32_t ti = 0, round = 0;
     bool ok = true;
-    for (long long item = blockIdx.x; item < q.items && ok; item += gridDim.x) {
-      const int nops = item_nops(q, item);
-      if (expm) {
-        // X' = xscale (A_0 + sum_k u_k A_k), u_k = maxA_k sin(base[b][k][t])  (init_tf_ops_weight, :168-185)
+    for (long long it0 = (long long)blockIdx.x * ILV; it0 < q.items && ok; it0 += (long long)gridDim.x * ILV, ++round) {
+      const int nz = (int)min((long long)ILV, q.items - it0);
+      const int nops = item_nops(q, it0);
+      // generators of one round: X' = xscale (A_0 + sum_k u_k A_k), u_k = maxA_k sin(base[b][k][t])  (init_tf_ops_weight,
+      // :168-185), into the X slot of that round's parity; round r + 1 is assembled in the middle of round r
+      auto build_x = [&](long long bi0, int bnz, int rpar) {
+       for (int z = 0; z < bnz; ++z) {
+        const long long item = bi0 + z;
         const long long b = item / q.T;
         const int t = (int)(item % q.T);
+        epi_bar();                                   // wts of the previous item are no longer read
         if (et <= q.K) wts[et] = et == 0 ? q.xscale : (float)(q.maxA[et - 1] * sin(q.ctrl[((size_t)b * q.K + et - 1) * q.T + t])) * q.xscale;
         epi_bar();
-        __half* X = q.base[TC_CLS_SCR] + (size_t)((long long)blockIdx.x * TC_NSLOT) * mat;
+        __half* X = q.base[TC_CLS_SCR] + (size_t)(((long long)blockIdx.x * ILV + z) * TC_NSLOT + (rpar ? 4 : 0)) * mat;
         const int l16 = ld >> 4;
         const size_t nn = (size_t)n * n;
         for (int i16 = et; i16 < n * l16; i16 += NEPI) {
           const int r = i16 / l16, c16 = (i16 - r * l16) * 16;
           float re[16], im[16];
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc) {
-            float xr = 0.f, xi = 0.f;
-            if (c16 + cc < n) {
-              for (int k = 0; k <= q.K; ++k) {
-                const float2 a = __ldg(q.A_f + (size_t)k * nn + (size_t)r * n + c16 + cc);
-                xr = fmaf(wts[k], a.x, xr); xi = fmaf(wts[k], a.y, xi);
+          for (int cc = 0; cc < 16; ++cc) re[cc] = im[cc] = 0.f;
+          // 16 consecutive complex entries of A_k = 128 bytes: eight independent 16-byte loads per k, two k in flight
+          // (a per-element loop over k serialises on the load latency: 345k cycles per item at n = 216)
+          const bool full = c16 + 16 <= n && (n & 1) == 0;           // 16-byte alignment of the row segment
+          for (int k0 = 0; k0 <= q.K; k0 += 2) {
+            float4 v[2][8];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const int k = k0 + kk;
+              const float2* src = q.A_f + (size_t)k * nn + (size_t)r * n + c16;
+#pragma unroll
+              for (int h = 0; h < 8; ++h) {
+                if (k <= q.K && full) v[kk][h] = __ldg(reinterpret_cast<const float4*>(src) + h);
+                else if (k <= q.K) {
+                  const float2 a0 = c16 + 2 * h < n ? __ldg(src + 2 * h) : make_float2(0.f, 0.f);
+                  const float2 a1 = c16 + 2 * h + 1 < n ? __ldg(src + 2 * h + 1) : make_float2(0.f, 0.f);
+                  v[kk][h] = make_float4(a0.x, a0.y, a1.x, a1.y);
+                } else v[kk][h] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
             }
-            re[cc] = xr; im[cc] = xi;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const float w = k0 + kk <= q.K ? wts[k0 + kk] : 0.f;
+#pragma unroll
+              for (int h = 0; h < 8; ++h) {
+                re[2 * h] = fmaf(w, v[kk][h].x, re[2 * h]); im[2 * h] = fmaf(w, v[kk][h].y, im[2 * h]);
+                re[2 * h + 1] = fmaf(w, v[kk][h].z, re[2 * h + 1]); im[2 * h + 1] = fmaf(w, v[kk][h].w, im[2 * h + 1]);
+              }
+            }
           }
           store_planes16(X, plane, ld, r, c16, re, im);
         }
+       }
         asm volatile("fence.proxy.async;" ::: "memory");
-        for (int i = 0; i < NQ; ++i) mbar_arrive(&bar_done[i]);
-        epi_bar();                                   // X is read back (elementwise source) by other threads than its writers
-      } else if (q.prog == TC_PROG_CHAIN) {
-        if (et == 0) q.scal[(size_t)item * 8 + 5] = 0.0;
+        epi_bar();                                   // every thread's stores precede the counter bump; X is read back (elementwise
+        if (et == 0)                                 // source) by other threads than its writers
+          asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(&xdone_cnt)) : "memory");
+      };
+      if (expm && round == 0) build_x(it0, nz, 0);
+      if (q.prog == TC_PROG_CHAIN) {
+        if (et == 0) q.scal[(size_t)it0 * 8 + 5] = 0.0;
         epi_bar();
       }
-      for (int j = 0; j < nops && ok; ++j) {
-        OpR o; make_op(q, item, j, nops, o);
+      for (int j = 0; j < nops && ok; ++j)
+       for (int z = 0; z < nz && ok; ++z) {
+        if (expm && z == 0 && j == (nops > 2 ? 2 : nops - 1)) {      // next round's generators, off the round boundary
+          const long long nx0 = it0 + (long long)gridDim.x * ILV;
+          if (nx0 < q.items) build_x(nx0, (int)min((long long)ILV, q.items - nx0), (int)((round + 1) & 1));
+        }
+        const long long item = it0 + z;
+        OpR o; make_op(q, item, j, nops, z, (int)(round & 1), o);
         const __half* E = o.e_cls >= 0 ? q.base[o.e_cls] + (size_t)o.e_idx * mat : nullptr;
         __half* D1 = o.d1_cls >= 0 ? q.base[o.d1_cls] + (size_t)o.d1_idx * mat : nullptr;
         __half* D2 = o.d2_cls >= 0 ? q.base[o.d2_cls] + (size_t)o.d2_idx * mat : nullptr;
@@ -450,34 +507,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
             const int row = rb * 128 + lrow;
             const bool vrow = row < n;
             if (nh == 0) { sr = 0.0; si = 0.0; }
-            // elementwise source (b_j X of a Horner step, 2 E of a squaring): two chunks in flight, the first two fetched
-            // while the MMAs of this tile still run
-            uint32_t e0[4][8], e1[4][8];
+            // elementwise source (b_j X of a Horner step, 2 E of a squaring): the first chunk is fetched while the MMAs of
+            // this tile still run, the next one right after the current one has been unpacked
+            uint32_t e0[4][8];
             const bool ldE = useE && vrow;
-            auto fetchE = [&](int c0, uint32_t (&e)[4][8]) {
+            auto fetchE = [&](int c0) {
               if (ldE && c0 < nt) {
                 const __half* p0 = E + (size_t)row * ld + cbase + c0;
 #pragma unroll
-                for (int pl = 0; pl < 4; ++pl) ldg256(p0 + pl * plane, e[pl]);
+                for (int pl = 0; pl < 4; ++pl) ldg256(p0 + pl * plane, e0[pl]);
               }
             };
-            fetchE(16 * half, e0);
-            fetchE(16 * half + CSTEP, e1);
+            fetchE(16 * half);
             long long c0t = prof ? clock64() : 0;
             ok = __all_sync(0xffffffffu, mbar_wait(&bar_tfull[buf], use & 1, dead));
             if (!ok) break;
             if (prof) { const long long c1t = clock64(); t_wait0 += c1t - c0t; c0t = c1t; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // one 16-column chunk: accumulator rows out of TMEM, elementwise term from `e`, split, store; `e` is refilled
-            // for the chunk two ahead
-            auto chunk = [&](int c0, uint32_t (&e)[4][8]) {
+            // one 16-column chunk: accumulator rows out of TMEM, elementwise term, split, store
+            for (int c0 = 16 * half; c0 < nt; c0 += CSTEP) {
               uint32_t ur[16], ui[16];
               tmem_ld16(lane_addr + (uint32_t)c0, ur);
               tmem_ld16(lane_addr + (uint32_t)(DIOFF + c0), ui);
               float er[16], ei[16];
-              if (useE) { unpack16(e[0], e[1], er); unpack16(e[2], e[3], ei); fetchE(c0 + 2 * CSTEP, e); }
+              if (useE) { unpack16(e0[0], e0[1], er); unpack16(e0[2], e0[3], ei); fetchE(c0 + CSTEP); }
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-              if (!vrow) return;
+              if (!vrow) continue;
               const int col = cbase + c0;
 #pragma unroll
               for (int comp = 0; comp < 2; ++comp) {      // Re: planes 0,1; Im: planes 2,3
@@ -512,10 +567,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
                     sr += xr; si += xi;
                   }
               }
-            };
-            for (int c0 = 16 * half; c0 < nt; c0 += 2 * CSTEP) {
-              chunk(c0, e0);
-              if (c0 + CSTEP < nt) chunk(c0 + CSTEP, e1);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&bar_tempty[buf]);
@@ -535,7 +586,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
               epi_bar();
             }
             asm volatile("fence.proxy.async;" ::: "memory");
-            mbar_arrive(&bar_done[rb * NH + nh]);      // this quadrant of the product's outputs is complete
+            epi_bar();                                 // this quadrant of the product's outputs is complete: all threads' stores,
+            if (et == 0)                               // then one release-increment of its counter
+              asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(&done_cnt[rb * NH + nh])) : "memory");
             if (prof) t_work += clock64() - c0t;
           }
       }
@@ -707,6 +760,7 @@ cudaError_t tc_launch(const TcParams& q_in, const TcMaps& maps, const TcGeom& g,
   cudaError_t e = cudaFuncSetAttribute(k_tc_prog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
   if (grid < 1) grid = 1;
+  if (q.ilv < 1 || q.prog != TC_PROG_EXPM) q.ilv = 1;
   k_tc_prog<<<grid, NTHREADS, g.smem, st>>>(q, maps);
   return cudaGetLastError();
 }

@@ -17,7 +17,7 @@
 #include <vector>
 
 #define TC_EU 13                 // scale exponent of unitary-like matrices (entries <= ~1 -> <= 8192 stored)
-#define TC_NSLOT 4               // per-CTA scratch matrices: X, Y, Z ping-pong
+#define TC_NSLOT 5               // per-item scratch matrices: X (even rounds), Y, Z ping-pong, X (odd rounds)
 #define TC_SLOT_OUT 15           // "the program's output matrix" as an expm-op destination
 #define TC_MAX_N 256
 
@@ -45,6 +45,7 @@ struct TcParams {
   int prog;
   int n, ld, N16, NT0, NH, NGT, DIOFF, NBUF, RB, KBLK, stages, tmem_cols;
   long long items;
+  int ilv;                       // items interleaved per CTA (EXPM: 2 -- consecutive products of the stream are independent)
   __half* base[TC_NCLS];         // plane-set arrays; matrix i of a class at base + i * 4 n ld
   // EXPM
   int nops; const TcExpmOp* ops;

@@ -53,7 +53,7 @@ struct Dev {
 
 static void dev_setup(Dev& d, int n, size_t nP, size_t nSeg, int grid) {
   if (!tc_geometry(n, &d.g)) { printf("{\"error\": \"geometry\"}\n"); exit(0); }
-  d.count[TC_CLS_SCR] = (size_t)grid * TC_NSLOT;
+  d.count[TC_CLS_SCR] = (size_t)grid * 2 * TC_NSLOT;          // two interleaved items per CTA in the expm program
   d.count[TC_CLS_P] = nP;
   d.count[TC_CLS_SEG] = nSeg;
   d.count[TC_CLS_CONST] = 2;
@@ -225,6 +225,7 @@ static void expm_upload(const ExpmProblem& P, ExpmDev& e, TcParams& q) {
   CK(cudaMemcpy(e.A_f, Af.data(), Af.size() * sizeof(float2), cudaMemcpyHostToDevice));
   e.xscale = (float)ldexp(1.0, eX - P.s);
   q.prog = TC_PROG_EXPM; q.items = (long long)P.B * P.T;
+  q.ilv = 2;
   q.nops = e.nops; q.ops = e.ops; q.K = P.K; q.T = P.T; q.ctrl = e.ctrl; q.maxA = e.maxA; q.A_f = e.A_f; q.xscale = e.xscale;
 }
 
@@ -317,8 +318,8 @@ static void time_expm(int n, int K, int T, int B, int p, int s, int reps) {
     CK(cudaMemcpy(h.data(), prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     double a[8] = {0};
     for (int c = 0; c < g2; ++c) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)c * 8 + i] / g2;
-    printf("{\"test\": \"roles\", \"n\": %d, \"producer_wait_opdone_Mcyc\": %.2f, \"producer_wait_empty_Mcyc\": %.2f, \"mma_wait_tmem_empty_Mcyc\": %.2f, \"mma_wait_full_Mcyc\": %.2f, \"epi_wait_tmem_full_Mcyc\": %.2f, \"epi_work_Mcyc\": %.2f}\n",
-           n, a[0] * 1e-6, a[1] * 1e-6, a[2] * 1e-6, a[3] * 1e-6, a[4] * 1e-6, a[5] * 1e-6);
+    printf("{\"test\": \"roles\", \"n\": %d, \"producer_wait_opdone_Mcyc\": %.2f, \"producer_wait_empty_Mcyc\": %.2f, \"mma_wait_tmem_empty_Mcyc\": %.2f, \"mma_wait_full_Mcyc\": %.2f, \"epi_wait_tmem_full_Mcyc\": %.2f, \"epi_work_Mcyc\": %.2f, \"producer_wait_prologue_Mcyc\": %.2f, \"producer_wait_prev_product_Mcyc\": %.2f}\n",
+           n, a[0] * 1e-6, a[1] * 1e-6, a[2] * 1e-6, a[3] * 1e-6, a[4] * 1e-6, a[5] * 1e-6, a[6] * 1e-6, a[7] * 1e-6);
   }
   const double alg = 8.0 * n * n * n * (double)(p - 1 + s) * (double)B * T;       // SURVEY 8d count
   const double issued = 8.0 * n * n * n * (double)e.nops * (double)B * T;
@@ -329,11 +330,47 @@ static void time_expm(int n, int K, int T, int B, int p, int s, int reps) {
   dev_free(d);
 }
 
+// streaming throughput of INDEPENDENT products (TC_PROG_GEMM): no dependency chain, no elementwise source
+static void time_gemm(int n, int items, int reps) {
+  cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
+  const int grid = std::min(items, pr.multiProcessorCount);
+  Dev d; dev_setup(d, n, 2 * (size_t)items, items, grid);
+  CK(cudaMemset(d.base[TC_CLS_P], 0, 2 * (size_t)items * d.g.mat_halfs * sizeof(__half)));
+  TcParams q; fill_params(d, q);
+  q.prog = TC_PROG_GEMM; q.items = items;
+  unsigned long long* prof; CK(cudaMalloc((void**)&prof, (size_t)grid * 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(prof, 0, (size_t)grid * 8 * sizeof(unsigned long long)));
+  q.prof = prof;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(tc_launch(q, d.maps, d.g, grid, 0));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  for (int r = 0; r < reps; ++r) CK(tc_launch(q, d.maps, d.g, grid, 0));
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= reps;
+  std::vector<unsigned long long> h((size_t)grid * 8);
+  CK(cudaMemcpy(h.data(), prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  double a[8] = {0};
+  for (int c = 0; c < grid; ++c) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)c * 8 + i] / grid;
+  printf("{\"test\": \"time_gemm\", \"n\": %d, \"items\": %d, \"ms\": %.4f, \"complex_tflops\": %.2f, \"producer_wait_done_Mcyc\": %.2f, \"producer_wait_empty_Mcyc\": %.2f, \"mma_wait_tmem_empty_Mcyc\": %.2f, \"mma_wait_full_Mcyc\": %.2f, \"epi_wait_tmem_full_Mcyc\": %.2f, \"epi_work_Mcyc\": %.2f, \"timeout\": %d}\n",
+         n, items, ms, 8.0 * n * n * n * items / ms * 1e-9, a[0] * 1e-6, a[1] * 1e-6, a[2] * 1e-6, a[3] * 1e-6, a[4] * 1e-6, a[5] * 1e-6, dev_err(d));
+  fflush(stdout);
+  dev_free(d);
+}
+
 int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "all";
   if (what == "gemm" || what == "all") {
     const int ns[] = {16, 36, 64, 100, 128, 216, 256};
     for (int n : ns) test_gemm(n, 3, 0, 0, 0, "default");
+  }
+  if (what == "timegemm") {
+    time_gemm(216, 148 * 24, 2);
+    time_gemm(128, 148 * 64, 2);
+    time_gemm(256, 148 * 16, 2);
+    time_gemm(64, 148 * 128, 2);
   }
   if (what == "time1" && argc >= 9)   // time1 n K T B p s reps
     time_expm(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]));
