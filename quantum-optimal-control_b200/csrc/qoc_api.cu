@@ -485,6 +485,11 @@ static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   q.prog = TC_PROG_EXPM; q.items = (long long)p.B * p.T; q.ilv = QOC_TC_ILV;
   q.nops = h->tc_nops; q.ops = h->tc_ops; q.K = p.K; q.T = p.T; q.ctrl = p.base; q.maxA = p.maxA; q.A_f = h->A_f; q.xscale = h->tc_xscale;
   ++h->launches;
+  static const int small_on = getenv("QOC_B200_TC_SMALL") ? atoi(getenv("QOC_B200_TC_SMALL")) : 1;
+  if (small_on && tc_small_supported(p.n)) {       // n <= 64: operands resident in shared memory (qoc_tc_small.cu)
+    CUDA_TRY(h, tc_small_launch_expm(q, p.n, h->sm_count, st));
+    return QOC_OK;
+  }
   {
     const long long rounds = (q.items + QOC_TC_ILV - 1) / QOC_TC_ILV;
     CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(rounds < h->tc_grid ? rounds : h->tc_grid), st));

@@ -20,6 +20,7 @@
 #define TC_NSLOT 5               // per-item scratch matrices: X (even rounds), Y, Z ping-pong, X (odd rounds)
 #define TC_SLOT_OUT 15           // "the program's output matrix" as an expm-op destination
 #define TC_MAX_N 256
+#define TC_MAX_OPS 96           // products of one propagator program (Paterson-Stockmeyer steps + squarings)
 
 enum { TC_CLS_SCR = 0, TC_CLS_P = 1, TC_CLS_SEG = 2, TC_CLS_CONST = 3, TC_NCLS = 4 };
 // programs: an item is a sequence of dependent complex products run by one CTA
@@ -73,5 +74,8 @@ void tc_build_expm_ops(int p, int s, int eX, int eY, std::vector<TcExpmOp>& ops)
 // scale exponents from the entrywise bound |X| <= xmax (max entry) and ||X||_2 <= theta
 void tc_pick_scales(double xmax, double theta, int* eX, int* eY);
 cudaError_t tc_launch(const TcParams& q, const TcMaps& maps, const TcGeom& g, int grid, cudaStream_t st);
+// small Hilbert dimensions (n <= 64): the propagator program with shared-memory-resident operands (qoc_tc_small.cu)
+bool tc_small_supported(int n);
+cudaError_t tc_small_launch_expm(const TcParams& q, int n, int sm_count, cudaStream_t st);
 // plane-set <-> complex double converters (host side of tests, constants upload)
 void tc_pack_host(const double* z /* [n][n] (re,im) */, int n, int ld, int e, __half* out /* [4][n][ld] */);

@@ -229,6 +229,7 @@ static void expm_upload(const ExpmProblem& P, ExpmDev& e, TcParams& q) {
   q.nops = e.nops; q.ops = e.ops; q.K = P.K; q.T = P.T; q.ctrl = e.ctrl; q.maxA = e.maxA; q.A_f = e.A_f; q.xscale = e.xscale;
 }
 
+static bool g_small = false;      // run the propagator program on the shared-memory-resident kernel (n <= 64)
 static void test_expm_chain(int n, int K, int T, int B, int p, int s, int L, double norm) {
   cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
   ExpmProblem P; make_problem(P, n, K, T, B, p, s, norm);
@@ -238,7 +239,8 @@ static void test_expm_chain(int n, int K, int T, int B, int p, int s, int L, dou
   Dev d; dev_setup(d, n, (size_t)B * T, (size_t)B * S, grid);
   TcParams q; fill_params(d, q);
   ExpmDev e; expm_upload(P, e, q);
-  CK(tc_launch(q, d.maps, d.g, (int)std::min<long long>(grid, q.items), 0));
+  if (g_small && tc_small_supported(n)) CK(tc_small_launch_expm(q, n, pr.multiProcessorCount, 0));
+  else CK(tc_launch(q, d.maps, d.g, (int)std::min<long long>(grid, q.items), 0));
   CK(cudaDeviceSynchronize());
   double err = 0; int nan = 0;
   std::vector<std::vector<cd>> Pref((size_t)B * T);
@@ -250,8 +252,8 @@ static void test_expm_chain(int n, int K, int T, int B, int p, int s, int L, dou
       for (auto& x : G) if (!(std::abs(x) < 1e30)) { ++nan; x = cd(0, 0); }
       err = std::max(err, max_abs_diff(Pref[(size_t)b * T + t], G));
     }
-  printf("{\"test\": \"expm\", \"n\": %d, \"K\": %d, \"T\": %d, \"B\": %d, \"p\": %d, \"s\": %d, \"nops\": %d, \"max_abs_err\": %.3e, \"nan\": %d, \"timeout\": %d, \"ok\": %s}\n",
-         n, K, T, B, p, s, e.nops, err, nan, dev_err(d), (err < 2e-5 && !nan) ? "true" : "false");
+  printf("{\"test\": \"expm%s\", \"n\": %d, \"K\": %d, \"T\": %d, \"B\": %d, \"p\": %d, \"s\": %d, \"nops\": %d, \"max_abs_err\": %.3e, \"nan\": %d, \"timeout\": %d, \"ok\": %s}\n",
+         (g_small && tc_small_supported(n)) ? "_small" : "", n, K, T, B, p, s, e.nops, err, nan, dev_err(d), (err < 2e-5 && !nan) ? "true" : "false");
   fflush(stdout);
   // segment products + chain
   double2* Ufin; double* scal;
@@ -302,18 +304,25 @@ static void time_expm(int n, int K, int T, int B, int p, int s, int reps) {
   ExpmDev e; expm_upload(P, e, q);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const int g2 = (int)std::min<long long>(grid, q.items);
+  const bool small = g_small && tc_small_supported(n);
   unsigned long long* prof; CK(cudaMalloc((void**)&prof, (size_t)g2 * 8 * sizeof(unsigned long long)));
   CK(cudaMemset(prof, 0, (size_t)g2 * 8 * sizeof(unsigned long long)));
   q.prof = prof;
-  CK(tc_launch(q, d.maps, d.g, g2, 0));
+  if (small) CK(tc_small_launch_expm(q, n, pr.multiProcessorCount, 0)); else CK(tc_launch(q, d.maps, d.g, g2, 0));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r) CK(tc_launch(q, d.maps, d.g, g2, 0));
+  for (int r = 0; r < reps; ++r) { if (small) CK(tc_small_launch_expm(q, n, pr.multiProcessorCount, 0)); else CK(tc_launch(q, d.maps, d.g, g2, 0)); }
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
   ms /= reps;
-  {   // per-role cycle attribution of the last launch (averages over CTAs)
+  if (small) {
+    std::vector<unsigned long long> h((size_t)g2 * 8);
+    CK(cudaMemcpy(h.data(), prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    printf("{\"test\": \"small_epilogue_cycles_cta0\", \"n\": %d, \"x_assembly\": %llu, \"wait_acc\": %llu, \"tmem_ld\": %llu, \"math_stores\": %llu, \"fence_arrive\": %llu, \"kernel_cycles\": %.0f}\n",
+           n, h[0], h[1], h[2], h[3], h[4], ms * 1.965e6);
+  }
+  if (!small) {   // per-role cycle attribution of the last launch (averages over CTAs)
     std::vector<unsigned long long> h((size_t)g2 * 8);
     CK(cudaMemcpy(h.data(), prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     double a[8] = {0};
@@ -323,8 +332,8 @@ static void time_expm(int n, int K, int T, int B, int p, int s, int reps) {
   }
   const double alg = 8.0 * n * n * n * (double)(p - 1 + s) * (double)B * T;       // SURVEY 8d count
   const double issued = 8.0 * n * n * n * (double)e.nops * (double)B * T;
-  printf("{\"test\": \"time_expm\", \"n\": %d, \"T\": %d, \"B\": %d, \"p\": %d, \"s\": %d, \"nops\": %d, \"grid\": %d, \"stages\": %d, \"ms\": %.4f, \"us_per_item\": %.3f, \"alg_tflops\": %.2f, \"issued_complex_tflops\": %.2f, \"timeout\": %d}\n",
-         n, T, B, p, s, e.nops, g2, g.stages, ms, 1e3 * ms / ((double)B * T) , alg / ms * 1e-9, issued / ms * 1e-9, dev_err(d));
+  printf("{\"test\": \"time_expm%s\", \"n\": %d, \"T\": %d, \"B\": %d, \"p\": %d, \"s\": %d, \"nops\": %d, \"grid\": %d, \"stages\": %d, \"ms\": %.4f, \"us_per_item\": %.3f, \"alg_tflops\": %.2f, \"issued_complex_tflops\": %.2f, \"timeout\": %d}\n",
+         small ? "_small" : "", n, T, B, p, s, e.nops, g2, g.stages, ms, 1e3 * ms / ((double)B * T) , alg / ms * 1e-9, issued / ms * 1e-9, dev_err(d));
   fflush(stdout);
   cudaFree(e.ops); cudaFree(e.ctrl); cudaFree(e.maxA); cudaFree(e.A_f);
   dev_free(d);
@@ -365,6 +374,24 @@ int main(int argc, char** argv) {
   if (what == "gemm" || what == "all") {
     const int ns[] = {16, 36, 64, 100, 128, 216, 256};
     for (int n : ns) test_gemm(n, 3, 0, 0, 0, "default");
+  }
+  if (what == "small") {
+    g_small = true;
+    const int ns[] = {8, 16, 24, 30, 32, 36, 40, 48, 64};
+    for (int n : ns) test_expm_chain(n, 2, 6, 3, 6, 3, 4, 0.8);
+    test_expm_chain(36, 4, 40, 7, 8, 2, 16, 0.8);
+    test_expm_chain(30, 4, 25, 5, 7, 3, 16, 0.8);
+    test_expm_chain(12, 2, 9, 3, 1, 0, 4, 0.01);
+    test_expm_chain(20, 2, 9, 3, 2, 0, 4, 0.1);
+    test_expm_chain(20, 2, 9, 3, 5, 0, 4, 0.3);
+    time_expm(36, 4, 512, 148, 8, 2, 3);
+    time_expm(64, 2, 128, 148, 8, 2, 3);
+    time_expm(30, 4, 512, 148, 7, 3, 3);
+    time_expm(16, 2, 1024, 148, 8, 2, 3);
+  }
+  if (what == "small1" && argc >= 9) {   // small1 n K T B p s reps
+    g_small = true;
+    time_expm(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]));
   }
   if (what == "timegemm") {
     time_gemm(216, 148 * 24, 2);
