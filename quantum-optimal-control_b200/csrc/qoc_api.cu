@@ -482,7 +482,9 @@ static void tc_base_params(qoc_handle_t h, TcParams& q) {
 static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   TcParams q;
   tc_base_params(h, q);
-  q.prog = TC_PROG_EXPM; q.items = (long long)p.B * p.T; q.ilv = QOC_TC_ILV;
+  q.prog = TC_PROG_EXPM; q.items = (long long)p.B * p.T;
+  q.ilv = p.n > 128 ? 1 : QOC_TC_ILV;               // n > 128: four tiles per product already decouple MMA and epilogue, and one
+                                                    // item per CTA keeps the scratch working set (148 x 1.5 MB) near the L2 size
   q.nops = h->tc_nops; q.ops = h->tc_ops; q.K = p.K; q.T = p.T; q.ctrl = p.base; q.maxA = p.maxA; q.A_f = h->A_f; q.xscale = h->tc_xscale;
   ++h->launches;
   static const int small_on = getenv("QOC_B200_TC_SMALL") ? atoi(getenv("QOC_B200_TC_SMALL")) : 1;
@@ -491,7 +493,7 @@ static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
     return QOC_OK;
   }
   {
-    const long long rounds = (q.items + QOC_TC_ILV - 1) / QOC_TC_ILV;
+    const long long rounds = (q.items + q.ilv - 1) / q.ilv;
     CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(rounds < h->tc_grid ? rounds : h->tc_grid), st));
   }
   return QOC_OK;

@@ -225,7 +225,7 @@ static void expm_upload(const ExpmProblem& P, ExpmDev& e, TcParams& q) {
   CK(cudaMemcpy(e.A_f, Af.data(), Af.size() * sizeof(float2), cudaMemcpyHostToDevice));
   e.xscale = (float)ldexp(1.0, eX - P.s);
   q.prog = TC_PROG_EXPM; q.items = (long long)P.B * P.T;
-  q.ilv = 2;
+  q.ilv = getenv("TC_ILV") ? atoi(getenv("TC_ILV")) : 2;
   q.nops = e.nops; q.ops = e.ops; q.K = P.K; q.T = P.T; q.ctrl = e.ctrl; q.maxA = e.maxA; q.A_f = e.A_f; q.xscale = e.xscale;
 }
 
