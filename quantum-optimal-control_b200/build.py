@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libqoc_b200.so")
-SOURCES = ["qoc_mma_f64.cu", "qoc_large_f64.cu", "qoc_tc_tf32.cu", "qoc_tc_f16.cu", "qoc_tc_small.cu", "qoc_plane_sweep.cu", "qoc_sweeps.cu", "qoc_vecsweep.cu", "qoc_api.cu"]
+SOURCES = ["qoc_mma_f64.cu", "qoc_large_f64.cu", "qoc_tc_tf32.cu", "qoc_tc_f16.cu", "qoc_tc_small.cu", "qoc_tc_pair.cu", "qoc_plane_sweep.cu", "qoc_sweeps.cu", "qoc_vecsweep.cu", "qoc_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "--use_fast_math=false"]
 

@@ -543,6 +543,32 @@ const char* tc_make_map(CUtensorMap* map, const void* base, int n, int ld, unsig
   return nullptr;
 }
 
+const char* tc_make_store_map(CUtensorMap* map, const void* base, int n, int ld, unsigned long long n_mats) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p ||
+        qr != cudaDriverEntryPointSuccess)
+      return "cuTensorMapEncodeTiled is not available from the driver";
+    fn = (PFN_encodeTiled)p;
+  }
+  // columns up to the row pitch: the padding columns of a result are written (zeros), as the thread-per-row stores do
+  const cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)n, 4, (cuuint64_t)n_mats};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)n * ld * 2, (cuuint64_t)4 * n * ld * 2};
+  const cuuint32_t box[4] = {16, 32, 4, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    static char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)r);
+    return msg;
+  }
+  return nullptr;
+}
+
 void tc_pick_scales(double xmax, double theta, int* eX, int* eY) {
   // stored magnitudes stay below 2^14 = 16384 (fp16 overflows at 65504)
   auto pick = [](double bound) {

@@ -42,6 +42,10 @@ struct TcMaps {                  // TMA descriptors per buffer class
   CUtensorMap b[TC_NCLS];        // B form: box {64 n, 32 k, 4 planes, 1},     SWIZZLE_128B (MN-major operand tiles)
 };
 
+struct TcStoreMaps {             // epilogue stores of the pair kernel: box {16 columns, 32 rows, 4 planes, 1}, SWIZZLE_32B
+  CUtensorMap st[TC_NCLS];
+};
+
 struct TcParams {
   int prog;
   int n, ld, N16, NT0, NH, NGT, DIOFF, NBUF, RB, KBLK, stages, tmem_cols;
@@ -55,6 +59,7 @@ struct TcParams {
   int L, S, chain_cls, chain_len;
   double2* Ufin; double* scal;
   int* err_flag;
+  int tma_store;                 // pair kernel: results leave through shared-memory staging + TMA stores
   unsigned long long* prof;      // optional [grid][8] cycle counters (tools/tc_prog_test.cu)
   // shared-memory matrix descriptor fields (>> 4), overridable by the probe tool
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
@@ -77,5 +82,10 @@ cudaError_t tc_launch(const TcParams& q, const TcMaps& maps, const TcGeom& g, in
 // small Hilbert dimensions (n <= 64): the propagator program with shared-memory-resident operands (qoc_tc_small.cu)
 bool tc_small_supported(int n);
 cudaError_t tc_small_launch_expm(const TcParams& q, int n, int sm_count, cudaStream_t st);
+// 128 < n <= 256: the propagator program on CTA pairs (tcgen05 cta_group::2) in clusters of cs = 2 or 4 CTAs (qoc_tc_pair.cu)
+bool tc_pair_supported(int n);
+int tc_pair_max_clusters(int cs);
+cudaError_t tc_pair_launch_expm(const TcParams& q, const TcMaps& maps, const TcStoreMaps& smaps, const TcGeom& g, int cs, cudaStream_t st);
+const char* tc_make_store_map(CUtensorMap* map, const void* base, int n, int ld, unsigned long long n_mats);
 // plane-set <-> complex double converters (host side of tests, constants upload)
 void tc_pack_host(const double* z /* [n][n] (re,im) */, int n, int ld, int e, __half* out /* [4][n][ld] */);

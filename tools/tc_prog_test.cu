@@ -45,6 +45,7 @@ static double max_abs_diff(const std::vector<cd>& a, const std::vector<cd>& b) {
 struct Dev {
   TcGeom g;
   TcMaps maps;
+  TcStoreMaps smaps;
   __half* base[TC_NCLS];
   size_t count[TC_NCLS];
   int* err;
@@ -63,7 +64,8 @@ static void dev_setup(Dev& d, int n, size_t nP, size_t nSeg, int grid) {
     CK(cudaMemset(d.base[c], 0xff, bytes));        // NaN patterns: any read of unwritten data shows up
     const char* ea = tc_make_map(&d.maps.a[c], d.base[c], n, d.g.ld, d.count[c] ? d.count[c] : 1, false);
     const char* eb = tc_make_map(&d.maps.b[c], d.base[c], n, d.g.ld, d.count[c] ? d.count[c] : 1, true);
-    if (ea || eb) { printf("{\"error\": \"%s\"}\n", ea ? ea : eb); exit(0); }
+    const char* es = tc_make_store_map(&d.smaps.st[c], d.base[c], n, d.g.ld, d.count[c] ? d.count[c] : 1);
+    if (ea || eb || es) { printf("{\"error\": \"%s\"}\n", ea ? ea : (eb ? eb : es)); exit(0); }
   }
   CK(cudaMalloc((void**)&d.err, sizeof(int)));
   CK(cudaMemset(d.err, 0, sizeof(int)));
@@ -230,6 +232,16 @@ static void expm_upload(const ExpmProblem& P, ExpmDev& e, TcParams& q) {
 }
 
 static bool g_small = false;      // run the propagator program on the shared-memory-resident kernel (n <= 64)
+static int g_pair = 0;            // CTAs per cluster (2 / 4) of the cta_group::2 kernel for n > 128; 0 = single-CTA engine
+static cudaError_t launch_expm(const TcParams& q, const Dev& d, int n, int sms, int grid) {
+  if (g_small && tc_small_supported(n)) return tc_small_launch_expm(q, n, sms, 0);
+  if (g_pair && tc_pair_supported(n)) {
+    TcParams q2 = q;
+    q2.tma_store = getenv("TC_TST") ? atoi(getenv("TC_TST")) : 1;
+    return tc_pair_launch_expm(q2, d.maps, d.smaps, d.g, g_pair, 0);
+  }
+  return tc_launch(q, d.maps, d.g, grid, 0);
+}
 static void test_expm_chain(int n, int K, int T, int B, int p, int s, int L, double norm) {
   cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
   ExpmProblem P; make_problem(P, n, K, T, B, p, s, norm);
@@ -239,8 +251,7 @@ static void test_expm_chain(int n, int K, int T, int B, int p, int s, int L, dou
   Dev d; dev_setup(d, n, (size_t)B * T, (size_t)B * S, grid);
   TcParams q; fill_params(d, q);
   ExpmDev e; expm_upload(P, e, q);
-  if (g_small && tc_small_supported(n)) CK(tc_small_launch_expm(q, n, pr.multiProcessorCount, 0));
-  else CK(tc_launch(q, d.maps, d.g, (int)std::min<long long>(grid, q.items), 0));
+  CK(launch_expm(q, d, n, pr.multiProcessorCount, (int)std::min<long long>(grid, q.items)));
   CK(cudaDeviceSynchronize());
   double err = 0; int nan = 0;
   std::vector<std::vector<cd>> Pref((size_t)B * T);
@@ -308,10 +319,10 @@ static void time_expm(int n, int K, int T, int B, int p, int s, int reps) {
   unsigned long long* prof; CK(cudaMalloc((void**)&prof, (size_t)g2 * 8 * sizeof(unsigned long long)));
   CK(cudaMemset(prof, 0, (size_t)g2 * 8 * sizeof(unsigned long long)));
   q.prof = prof;
-  if (small) CK(tc_small_launch_expm(q, n, pr.multiProcessorCount, 0)); else CK(tc_launch(q, d.maps, d.g, g2, 0));
+  CK(launch_expm(q, d, n, pr.multiProcessorCount, g2));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r) { if (small) CK(tc_small_launch_expm(q, n, pr.multiProcessorCount, 0)); else CK(tc_launch(q, d.maps, d.g, g2, 0)); }
+  for (int r = 0; r < reps; ++r) CK(launch_expm(q, d, n, pr.multiProcessorCount, g2));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -332,8 +343,8 @@ static void time_expm(int n, int K, int T, int B, int p, int s, int reps) {
   }
   const double alg = 8.0 * n * n * n * (double)(p - 1 + s) * (double)B * T;       // SURVEY 8d count
   const double issued = 8.0 * n * n * n * (double)e.nops * (double)B * T;
-  printf("{\"test\": \"time_expm%s\", \"n\": %d, \"T\": %d, \"B\": %d, \"p\": %d, \"s\": %d, \"nops\": %d, \"grid\": %d, \"stages\": %d, \"ms\": %.4f, \"us_per_item\": %.3f, \"alg_tflops\": %.2f, \"issued_complex_tflops\": %.2f, \"timeout\": %d}\n",
-         small ? "_small" : "", n, T, B, p, s, e.nops, g2, g.stages, ms, 1e3 * ms / ((double)B * T) , alg / ms * 1e-9, issued / ms * 1e-9, dev_err(d));
+  printf("{\"test\": \"time_expm%s\", \"pair\": %d, \"n\": %d, \"T\": %d, \"B\": %d, \"p\": %d, \"s\": %d, \"nops\": %d, \"grid\": %d, \"stages\": %d, \"ms\": %.4f, \"us_per_item\": %.3f, \"alg_tflops\": %.2f, \"issued_complex_tflops\": %.2f, \"timeout\": %d}\n",
+         small ? "_small" : "", g_pair, n, T, B, p, s, e.nops, g2, g.stages, ms, 1e3 * ms / ((double)B * T) , alg / ms * 1e-9, issued / ms * 1e-9, dev_err(d));
   fflush(stdout);
   cudaFree(e.ops); cudaFree(e.ctrl); cudaFree(e.maxA); cudaFree(e.A_f);
   dev_free(d);
@@ -392,6 +403,18 @@ int main(int argc, char** argv) {
   if (what == "small1" && argc >= 9) {   // small1 n K T B p s reps
     g_small = true;
     time_expm(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]));
+  }
+  if (what == "pair" && argc >= 3) {      // pair <cs>: correctness of the cta_group::2 propagator kernel, then timing at the C4 item size
+    g_pair = atoi(argv[2]);
+    test_expm_chain(216, 3, 9, 2, 5, 8, 4, 3.0);
+    test_expm_chain(256, 2, 5, 2, 6, 3, 4, 0.8);
+    test_expm_chain(130, 2, 5, 2, 6, 3, 4, 0.8);
+    test_expm_chain(176, 2, 7, 3, 4, 2, 4, 0.8);
+    time_expm(216, 3, 16, 148, 5, 8, 3);
+  }
+  if (what == "pair1" && argc >= 10) {    // pair1 cs n K T B p s reps
+    g_pair = atoi(argv[2]);
+    time_expm(atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]), atoi(argv[9]));
   }
   if (what == "timegemm") {
     time_gemm(216, 148 * 24, 2);
