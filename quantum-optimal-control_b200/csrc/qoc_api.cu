@@ -467,6 +467,7 @@ static int tc_prepare(qoc_handle_t h, cudaStream_t st) {
   for (int c = 0; c < TC_NCLS; ++c) {
     const char* e = tc_make_map(&h->tmaps.a[c], base[c], d.n, g.ld, cnt[c], false);
     if (!e) e = tc_make_map(&h->tmaps.b[c], base[c], d.n, g.ld, cnt[c], true);
+    if (!e) e = tc_make_store_map(&h->tsmaps.st[c], base[c], d.n, g.ld, cnt[c]);
     if (e) { h->err = e; return QOC_ECUDA; }
   }
   h->tc_ready = true;
@@ -490,6 +491,14 @@ static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   static const int small_on = getenv("QOC_B200_TC_SMALL") ? atoi(getenv("QOC_B200_TC_SMALL")) : 1;
   if (small_on && tc_small_supported(p.n)) {       // n <= 64: operands resident in shared memory (qoc_tc_small.cu)
     CUDA_TRY(h, tc_small_launch_expm(q, p.n, h->sm_count, st));
+    return QOC_OK;
+  }
+  static const int pair_on = getenv("QOC_B200_TC_PAIR") ? atoi(getenv("QOC_B200_TC_PAIR")) : 1;
+  if (pair_on && tc_pair_supported(p.n) && tc_pair_max_clusters(2) > 0) {
+    // 128 < n <= 256: CTA pairs (tcgen05 cta_group::2, M = 256), two items interleaved per pair, TMA-store epilogue (qoc_tc_pair.cu)
+    q.ilv = QOC_TC_ILV;
+    q.tma_store = 1;
+    CUDA_TRY(h, tc_pair_launch_expm(q, h->tmaps, h->tsmaps, h->tg, 2, st));
     return QOC_OK;
   }
   {

@@ -86,6 +86,7 @@ struct qoc_handle_s {
   // QOC_F16X2: tcgen05 / TMA program engine (qoc_tc_f16.cu)
   bool tc, tc_ready;
   TcGeom tg; TcMaps tmaps;
+  TcStoreMaps tsmaps;          // store-side descriptors of the pair kernel's epilogue
   __half *tc_seg, *tc_scr, *tc_const;     // plane-set arrays inside the workspace (P is h->P)
   TcExpmOp* tc_ops; int tc_nops; float tc_xscale;
   float2* A_f;                            // dense fp32 copy of A_0..A_K for the generator assembly

@@ -16,6 +16,8 @@
 #include "qoc_tc_dev.cuh"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
 
 namespace {
 
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
             uint32_t e0[4][8];
             const bool ldE = useE && vrow;
             auto fetchE = [&](int c0) {
-              if (ldE && c0 < nt) {
+              if (ldE && c0 < nt && !(q.tma_store & 4)) {
                 const __half* p0 = E + (size_t)row * ld + cbase + c0;
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl) ldg256(p0 + pl * plane, e0[pl]);
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0 && row0 < n) tma_store_4d(&smaps.st[dcls], stg, col, row0, 0, (int)(dd == 0 ? o.d1_idx : o.d2_idx));
+                if (lane == 0 && row0 < n && !(q.tma_store & 2)) tma_store_4d(&smaps.st[dcls], stg, col, row0, 0, (int)(dd == 0 ? o.d1_idx : o.d2_idx));
               }
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this tile's boxes are written, not just read
@@ -509,6 +511,7 @@ cudaError_t tc_pair_launch_expm(const TcParams& q_in, const TcMaps& maps, const 
   if (q.ilv < 1) q.ilv = 1;
   int ncl = tc_pair_max_clusters(cs);
   if (ncl < 1) return cudaErrorInvalidConfiguration;
+  if (getenv("QOC_B200_PAIR_CLUSTERS")) ncl = std::max(1, std::min(ncl, atoi(getenv("QOC_B200_PAIR_CLUSTERS"))));   // A/B knob: fewer items in flight
   const long long rounds_items = (q.items + q.ilv - 1) / q.ilv;
   if (ncl > rounds_items) ncl = (int)rounds_items;
   const size_t smem = (size_t)NSTAGE * STAGE_BYTES + (size_t)NEPIW * STG_BYTES + 1024;
