@@ -326,13 +326,22 @@ def measure(workload, dtype, B, steps, warmup, dev, local, world, rank, steps_T=
     if dtype == "f16x2":
         n16 = (n + 15) // 16 * 16
         rows = 128 * (2 if n > 128 else 1)
-        kpad = (n + 31) // 32 * 32
+        kpad = n16 if n <= 64 else (n + 31) // 32 * 32      # k-steps of 16 (shared-memory-resident operands) / stages of 32
         nprod = max(1, ps_products) + s                                 # products issued per (b,t)
         executed = 2.0 * rows * n16 * kpad * 12 * nprod * T * B         # 12 real MMAs (4 real products x 3 half-pairs) per k-step
-        kname = "k_tc_prog<EXPM> (tcgen05 kind::f16, TMA-fed, fp16-pair operands)"
+        if n <= 64:
+            ek = "k_tc_small_expm (tcgen05 kind::f16, shared-memory-resident fp16-pair operands)"
+            xk = "k_segprod<plane sets> + k_chain_mma (DMMA, fp64 segment matrices)"
+        elif n > 128:
+            ek = "k_tc_pair_expm (tcgen05 cta_group::2 kind::f16, TMA-fed fp16-pair operands, TMA-store epilogue)"
+            xk = "k_tc_prog<SEG> + k_tc_prog<CHAIN>"
+        else:
+            ek = "k_tc_prog<EXPM> (tcgen05 kind::f16, TMA-fed, fp16-pair operands)"
+            xk = "k_tc_prog<SEG> + k_tc_prog<CHAIN>"
+        kname = ek
         pipe = "fp16 tensor pipe via tcgen05 (3 MMAs per real product: h0 h0 + h0 h1 + h1 h0), fp32 accumulators in TMEM"
-        kernels = ("f16x2: expm = k_tc_prog<EXPM>; chain = k_plane_sweep<fwd> (states, fp64) on the handle's high-priority stream "
-                   "while k_tc_prog<SEG> + k_tc_prog<CHAIN> (U_final, unitary_scale) run on the caller's stream; costate = "
+        kernels = ("f16x2: expm = " + ek.split(" ")[0] + "; chain = k_plane_sweep<fwd> (states, fp64) on the handle's high-priority "
+                   "stream while " + xk + " (U_final, unitary_scale) run on the caller's stream; costate = "
                    "k_plane_sweep<rev>; grad / fwd_reduce / finalize as on the fp64 path")
     else:
         np_pad = 32 if dtype == "tf32x3" else (n + 7) // 8 * 8

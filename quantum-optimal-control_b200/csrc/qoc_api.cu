@@ -46,7 +46,7 @@ static WsLayout ws_layout(const qoc_dims_t& d, int sm_count, int Bc) {
   L.st_grad = off; off += align_up((size_t)d.B * d.K * d.T * sizeof(double));
   L.st_out = off; off += align_up((size_t)d.B * 4 * sizeof(double));
   L.seg = off;                                   // segment products of the re-associated U_final chain (n <= 64, fp64)
-  if (d.n <= 64 && !tc)
+  if (d.n <= 64)                                 // (also QOC_F16X2: its U_final branch for n <= 64 runs on the fp64 segment kernels)
     off += align_up((size_t)Bc * ((d.T + QOC_SEG_LEN - 1) / QOC_SEG_LEN) * nn * sizeof(cplx));
   L.scratch = off;
   if (d.n > 64 && !tc) off += align_up(qoc_large_scratch_elems(d.n, Bc, sm_count) * sizeof(cplx));
@@ -510,6 +510,19 @@ static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
 
 // U_final / unitary_scale: segment products (16 propagators each) + the chain over the segments, all on tcgen05
 static int tc_launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
+  static const int seg64 = getenv("QOC_B200_TC_SEG_F64") ? atoi(getenv("QOC_B200_TC_SEG_F64")) : 1;
+  const int S64 = (p.T + QOC_SEG_LEN - 1) / QOC_SEG_LEN;
+  if (seg64 && p.n <= 64 && S64 >= 4) {
+    // n <= 64: a product of this size leaves the streamed-operand engine idle most of the time (one 128-row MMA tile per
+    // 36 rows, a TMA round trip per product); the DMMA segment kernel reads the plane sets straight from the cache
+    // (widening h0 + h1 is exact) and runs beside the state sweeps; the segment matrices and the chain are fp64
+    QocParams q = p;
+    q.chain_no_psi = 1;
+    CUDA_TRY(h, qoc_launch_segprod_f64(p, h->NP, 2, QOC_SEG_LEN, S64, h->seg, st, &h->launches));
+    q.P = h->seg; q.T = S64;
+    CUDA_TRY(h, qoc_launch_chain_f64(q, h->NP, 0, st, &h->launches));
+    return QOC_OK;
+  }
   TcParams q;
   tc_base_params(h, q);
   const int L = QOC_TC_SEG_LEN, S = (p.T + L - 1) / L;

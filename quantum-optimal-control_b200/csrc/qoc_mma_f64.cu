@@ -707,8 +707,10 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_chain_mma(QocParams
 // ---------------------------------------------------------------------------------------------
 // PF32: the propagators are the tcgen05 path's fp32 planar padded [2][32][32] tiles; they are staged raw (double
 // buffered) and widened into the one swizzled operand buffer each step.
-template <int NP, int RB, int CB, bool PF32>
+// PFMT 2: the propagators are QOC_F16X2 plane sets [4][n][ld] fp16 (qoc_tc_f16.cuh; scale 2^13): staged raw, widened h0 + h1.
+template <int NP, int RB, int CB, int PFMT>
 __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p, int L, int S, cplx* __restrict__ seg_out) {
+  constexpr bool PF32 = PFMT != 0;                         // any raw-staged narrow format
   typedef MT<NP, RB, CB> T_;
   constexpr int G = T_::THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -724,17 +726,19 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
   const int seg = blockIdx.x / p.B, b = blockIdx.x - seg * p.B;
   const int t0 = seg * L, len = min(L, T - t0);
   const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + ((size_t)b * T + t0) * nn;
-  const float* Pgf = reinterpret_cast<const float*>(p.P) + ((size_t)b * T + t0) * 2048;
+  const int ldh = (n + 15) / 16 * 16;                      // plane-set row pitch (tc_ld)
+  const int raw_floats = PFMT == 2 ? 2 * n * ldh : 2048;   // one raw propagator, in 4-byte units
+  const float* Pgf = reinterpret_cast<const float*>(p.P) + ((size_t)b * T + t0) * raw_floats;
 
-  for (int i = tid; i < 3 * T_::MAT; i += G) Xb[i] = make_double2(0.0, 0.0);   // padding rows / columns stay zero
+  for (int i = tid; i < (PFMT ? 2 : 3) * T_::MAT; i += G) Xb[i] = make_double2(0.0, 0.0);   // padding rows / columns stay zero
   __syncthreads();
   const int dr = G / n, dc = G - dr * n, r_first = tid / n, c_first = tid - r_first * n;
   auto fetch = [&](int l, cplx* dst) {                     // P_{t0+l} -> swizzled operand buffer (PF32: raw staging)
     if (l < len) {
       if (PF32) {
-        const float* src = Pgf + (size_t)l * 2048;
-        float* stg = Pstage + (l & 1) * 2048;
-        for (int c = tid; c < 512; c += G) cp_async16(stg + 4 * c, src + 4 * c);
+        const float* src = Pgf + (size_t)l * raw_floats;
+        float* stg = Pstage + (l & 1) * raw_floats;
+        for (int c = tid; c < raw_floats / 4; c += G) cp_async16(stg + 4 * c, src + 4 * c);
       } else {
         const cplx* src = Pg + (size_t)l * nn + tid;
         int r = r_first, c = c_first;
@@ -748,10 +752,18 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
     cp_async_commit();
   };
   auto widen = [&](int l, cplx* dst) {                     // PF32: raw tile of step l -> swizzled double2 operand
-    const float* stg = Pstage + (l & 1) * 2048;
+    const float* stg = Pstage + (l & 1) * raw_floats;
+    const __half* sh = reinterpret_cast<const __half*>(stg);
+    const int pl = n * ldh;
+    const double sc = 1.0 / 8192.0;                        // 2^-TC_EU
     int r = r_first, c = c_first;
     for (int idx = tid; idx < nn; idx += G) {
-      dst[swz<NP>(r, c)] = make_double2((double)stg[r * 32 + c], (double)stg[1024 + r * 32 + c]);
+      if (PFMT == 2) {
+        const int o = r * ldh + c;
+        dst[swz<NP>(r, c)] = make_double2(((double)__half2float(sh[o]) + (double)__half2float(sh[pl + o])) * sc,
+                                          ((double)__half2float(sh[2 * pl + o]) + (double)__half2float(sh[3 * pl + o])) * sc);
+      } else
+        dst[swz<NP>(r, c)] = make_double2((double)stg[r * 32 + c], (double)stg[1024 + r * 32 + c]);
       r += dr; c += dc;
       if (c >= n) { c -= n; ++r; }
     }
@@ -793,10 +805,12 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
   }
 }
 
-template <int NP, int RB, int CB, bool PF32 = false>
+template <int NP, int RB, int CB, int PFMT = 0>
 cudaError_t launch_segprod(const QocParams& p, int L, int S, cplx* seg_out, cudaStream_t st) {
   typedef MT<NP, RB, CB> T_;
-  const size_t smem = PF32 ? (size_t)2 * T_::MAT * sizeof(cplx) + 2 * 2048 * sizeof(float) : (size_t)3 * T_::MAT * sizeof(cplx);
+  constexpr int PF32 = PFMT;
+  const size_t raw = PFMT == 2 ? (size_t)8 * p.n * ((p.n + 15) / 16 * 16) : (size_t)2048 * sizeof(float);
+  const size_t smem = PFMT ? (size_t)2 * T_::MAT * sizeof(cplx) + 2 * raw : (size_t)3 * T_::MAT * sizeof(cplx);
   cudaError_t e = cudaFuncSetAttribute(k_segprod<NP, RB, CB, PF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_segprod<NP, RB, CB, PF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1154,12 +1168,25 @@ cudaError_t qoc_launch_expm_f64(const QocParams& p, int NP, int sm_count, cudaSt
 cudaError_t qoc_launch_segprod_f64(const QocParams& p, int NP, int p_is_f32, int L, int S, cplx* seg_out, cudaStream_t st,
                                    int64_t* launches) {
   ++*launches;
+  if (p_is_f32 == 2) {                                // QOC_F16X2 plane sets, n <= 64
+    switch (NP) {
+      case 8: return launch_segprod<8, 1, 1, 2>(p, L, S, seg_out, st);
+      case 16: return launch_segprod<16, 2, 2, 2>(p, L, S, seg_out, st);
+      case 24: return launch_segprod<24, 1, 3, 2>(p, L, S, seg_out, st);
+      case 32: return launch_segprod<32, 2, 4, 2>(p, L, S, seg_out, st);
+      case 40: return launch_segprod<40, 1, 5, 2>(p, L, S, seg_out, st);
+      case 48: return launch_segprod<48, 2, 3, 2>(p, L, S, seg_out, st);
+      case 56: return launch_segprod<56, 1, 7, 2>(p, L, S, seg_out, st);
+      case 64: return launch_segprod<64, 2, 4, 2>(p, L, S, seg_out, st);
+    }
+    return cudaErrorInvalidValue;
+  }
   if (p_is_f32) {                                     // tcgen05 path: n <= 32
     switch (NP) {
-      case 8: return launch_segprod<8, 1, 1, true>(p, L, S, seg_out, st);
-      case 16: return launch_segprod<16, 2, 2, true>(p, L, S, seg_out, st);
-      case 24: return launch_segprod<24, 1, 3, true>(p, L, S, seg_out, st);
-      case 32: return launch_segprod<32, 2, 4, true>(p, L, S, seg_out, st);
+      case 8: return launch_segprod<8, 1, 1, 1>(p, L, S, seg_out, st);
+      case 16: return launch_segprod<16, 2, 2, 1>(p, L, S, seg_out, st);
+      case 24: return launch_segprod<24, 1, 3, 1>(p, L, S, seg_out, st);
+      case 32: return launch_segprod<32, 2, 4, 1>(p, L, S, seg_out, st);
     }
     return cudaErrorInvalidValue;
   }

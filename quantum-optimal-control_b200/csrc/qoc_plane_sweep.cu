@@ -62,7 +62,11 @@ DEVINL double2 widen2(uint32_t h0, uint32_t h1) {
 // by running many instances side by side.
 struct PlaneSweepShape { int nw, R, nst; size_t stage_halfs, smem; };
 
-PlaneSweepShape plane_sweep_shape(int n, int m) {
+static int sweep_vec_rows(int m) { return m <= 2 ? 2 : m <= 4 ? 4 : 8; }
+
+// B, sms: when ceil(B / sms) instances fit on an SM at once the whole batch runs in ONE wave (C3: 1024 instances on 148 SMs
+// need 7 per SM; at 6 per SM a second, nearly empty wave doubles the sweep time)
+PlaneSweepShape plane_sweep_shape(int n, int m, int B = 0, int sms = 0) {
   PlaneSweepShape s;
   const int ld = tc_ld(n);
   s.nw = n <= 64 ? 4 : n <= 128 ? 8 : 16;
@@ -72,15 +76,21 @@ PlaneSweepShape plane_sweep_shape(int n, int m) {
   const int rfull = (n + s.nw - 1) / s.nw * s.nw;
   s.R = r < rfull ? r : rfull;
   s.stage_halfs = (size_t)4 * s.R * ld;
-  const size_t vec = (size_t)2 * 8 * ld * sizeof(cplx);          // [2][8][2][ld/2]
+  const size_t vec = (size_t)2 * sweep_vec_rows(m) * ld * sizeof(cplx);          // [2][mv][2][ld/2]
   const size_t fixed = vec + 64 + 128;
-  const size_t budget = n <= 64 ? 36 * 1024 : n <= 128 ? 100 * 1024 : 220 * 1024;
+  size_t budget = n <= 64 ? 36 * 1024 : n <= 128 ? 100 * 1024 : 220 * 1024;
+  if (B > 0 && sms > 0) {
+    const int per_sm = (B + sms - 1) / sms;
+    if (per_sm >= 2 && per_sm <= 12) {
+      const size_t fit = (size_t)227 * 1024 / per_sm - 1024 - 256;      // 1 KB per CTA is reserved by the driver
+      if (fit < budget && fit >= fixed + 2 * s.stage_halfs * sizeof(__half)) budget = fit;
+    }
+  }
   int nst = budget > fixed ? (int)((budget - fixed) / (s.stage_halfs * sizeof(__half))) : 0;
   if (nst > 8) nst = 8;
   if (nst < 2 && fixed + 2 * s.stage_halfs * sizeof(__half) <= 220 * 1024) nst = 2;
   s.nst = nst;
   s.smem = fixed + (size_t)(nst > 0 ? nst : 0) * s.stage_halfs * sizeof(__half);
-  (void)m;
   return s;
 }
 
@@ -122,7 +132,8 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
   const size_t stage_halfs = (size_t)4 * R * ld;
   __half* ring = reinterpret_cast<__half*>(smem_raw);                                    // [NST][4][R][ld]
   cplx* vecs = reinterpret_cast<cplx*>(smem_raw + (size_t)NST * stage_halfs * sizeof(__half));   // [2][8][2][ld/2]: even / odd k split
-  uint64_t* full = reinterpret_cast<uint64_t*>(vecs + (size_t)2 * 8 * ld);               // [NST]
+  const int mv = m <= 2 ? 2 : m <= 4 ? 4 : 8;                                             // rows of a vector buffer
+  uint64_t* full = reinterpret_cast<uint64_t*>(vecs + (size_t)2 * mv * ld);               // [NST]
   const size_t plane = (size_t)n * ld, mat = 4 * plane;
   const __half* Pb = Pp + (size_t)b * T * mat;
   cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
   };
 
   // initial vectors, zero-padded
-  for (int e = tid; e < 2 * 8 * ld; e += NTH) vecs[e] = make_double2(0.0, 0.0);
+  for (int e = tid; e < 2 * mv * ld; e += NTH) vecs[e] = make_double2(0.0, 0.0);
   __syncthreads();
   for (int e = tid; e < m * n; e += NTH) {
     const int j = e / n, r = e - j * n;
@@ -204,8 +215,8 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
     // warp = row (rows warp, warp + 16 of the chunk), lane = pair of k; every shared-memory access is conflict-free
     // (P: consecutive 4-byte words; v: consecutive 16-byte elements of the even-k / odd-k halves)
     for (int step = 0; step < nsteps; ++step) {
-      const cplx* vc = vecs + (size_t)cur * 8 * ld;
-      cplx* vn = vecs + (size_t)(cur ^ 1) * 8 * ld;
+      const cplx* vc = vecs + (size_t)cur * mv * ld;
+      cplx* vn = vecs + (size_t)(cur ^ 1) * mv * ld;
       for (int c = 0; c < NC; ++c, ++g) {
         __syncthreads();                                   // previous chunk's stage is free; for c = 0: v(cur) complete
         if (tid == 0) prefetch(g + NST - 1);
@@ -258,8 +269,8 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
     const bool act = 2 * sg < m && 2 * cp < ld;
     for (int step = 0; step < nsteps; ++step) {
       const int t = T - 1 - step;
-      const cplx* vc = vecs + (size_t)cur * 8 * ld;
-      cplx* vn = vecs + (size_t)(cur ^ 1) * 8 * ld;
+      const cplx* vc = vecs + (size_t)cur * mv * ld;
+      cplx* vn = vecs + (size_t)(cur ^ 1) * mv * ld;
       double a[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};      // [state][col][re/im]
       for (int c = 0; c < NC; ++c, ++g) {
         __syncthreads();                                   // previous chunk's stage is free (and, for c = 0, v(cur) complete)
@@ -334,7 +345,9 @@ static cudaError_t launch_ps(const QocParams& p, const void* planes, const Plane
 cudaError_t qoc_launch_plane_sweep(const QocParams& p, const void* planes, int reverse, cudaStream_t st, int64_t* launches) {
   if (!qoc_plane_sweep_supported(p.n, p.m)) return cudaErrorNotSupported;
   ++*launches;
-  const PlaneSweepShape s = plane_sweep_shape(p.n, p.m);
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const PlaneSweepShape s = plane_sweep_shape(p.n, p.m, p.B, sms);
   if (reverse) return launch_ps<true, 8>(p, planes, s, st);
   if (p.m <= 2) return launch_ps<false, 2>(p, planes, s, st);
   if (p.m <= 4) return launch_ps<false, 4>(p, planes, s, st);
