@@ -488,12 +488,12 @@ static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
                                                     // item per CTA keeps the scratch working set (148 x 1.5 MB) near the L2 size
   q.nops = h->tc_nops; q.ops = h->tc_ops; q.K = p.K; q.T = p.T; q.ctrl = p.base; q.maxA = p.maxA; q.A_f = h->A_f; q.xscale = h->tc_xscale;
   ++h->launches;
-  static const int small_on = getenv("QOC_B200_TC_SMALL") ? atoi(getenv("QOC_B200_TC_SMALL")) : 1;
+  const int small_on = getenv("QOC_B200_TC_SMALL") ? atoi(getenv("QOC_B200_TC_SMALL")) : 1;     // read per call: tests flip it
   if (small_on && tc_small_supported(p.n)) {       // n <= 64: operands resident in shared memory (qoc_tc_small.cu)
     CUDA_TRY(h, tc_small_launch_expm(q, p.n, h->sm_count, st));
     return QOC_OK;
   }
-  static const int pair_on = getenv("QOC_B200_TC_PAIR") ? atoi(getenv("QOC_B200_TC_PAIR")) : 1;
+  const int pair_on = getenv("QOC_B200_TC_PAIR") ? atoi(getenv("QOC_B200_TC_PAIR")) : 1;
   if (pair_on && tc_pair_supported(p.n) && tc_pair_max_clusters(2) > 0) {
     // 128 < n <= 256: CTA pairs (tcgen05 cta_group::2, M = 256), two items interleaved per pair, TMA-store epilogue (qoc_tc_pair.cu)
     q.ilv = QOC_TC_ILV;
@@ -510,7 +510,7 @@ static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
 
 // U_final / unitary_scale: segment products (16 propagators each) + the chain over the segments, all on tcgen05
 static int tc_launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
-  static const int seg64 = getenv("QOC_B200_TC_SEG_F64") ? atoi(getenv("QOC_B200_TC_SEG_F64")) : 1;
+  const int seg64 = getenv("QOC_B200_TC_SEG_F64") ? atoi(getenv("QOC_B200_TC_SEG_F64")) : 1;
   const int S64 = (p.T + QOC_SEG_LEN - 1) / QOC_SEG_LEN;
   if (seg64 && p.n <= 64 && S64 >= 4) {
     // n <= 64: a product of this size leaves the streamed-operand engine idle most of the time (one 128-row MMA tile per

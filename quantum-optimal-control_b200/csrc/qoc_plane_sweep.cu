@@ -73,6 +73,10 @@ PlaneSweepShape plane_sweep_shape(int n, int m, int B = 0, int sms = 0) {
   const size_t stage_target = n <= 64 ? 8 * 1024 : n <= 128 ? 16 * 1024 : 24 * 1024;
   int r = (int)(stage_target / (8 * (size_t)ld)) / s.nw * s.nw;
   if (r < s.nw) r = s.nw;
+  {                                                              // two rows per warp and pass (forward sweep) when two stages fit
+    const size_t vec0 = (size_t)2 * sweep_vec_rows(m) * ld * sizeof(cplx);
+    if (r < 2 * s.nw && vec0 + 256 + 2 * (size_t)8 * 2 * s.nw * ld <= 220 * 1024) r = 2 * s.nw;
+  }
   const int rfull = (n + s.nw - 1) / s.nw * s.nw;
   s.R = r < rfull ? r : rfull;
   s.stage_halfs = (size_t)4 * s.R * ld;
@@ -223,17 +227,23 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
         while (!mbar_try_wait(&full[g % NST], (uint32_t)(g / NST) & 1u)) {}
         const uint32_t* St = reinterpret_cast<const uint32_t*>(ring + (size_t)(g % NST) * stage_halfs);
         const size_t pw = (size_t)R * lh;                  // plane stride in 32-bit words
+        // two rows per pass (rows rr and rr + NW of the chunk): the vector elements are read from shared memory once for both
+        // rows and 4 MS independent accumulation chains are in flight per lane
 #pragma unroll 1
-        for (int rr = warp; rr < R; rr += NW) {
+        for (int rr = warp; rr < R; rr += 2 * NW) {
           const int row = c * R + rr;
           if (row >= n) break;                             // warp-uniform
-          double a[2 * MS];
+          const bool two = rr + NW < R && row + NW < n;    // warp-uniform
+          double a[2 * MS], a2[2 * MS];
 #pragma unroll
-          for (int i = 0; i < 2 * MS; ++i) a[i] = 0.0;
+          for (int i = 0; i < 2 * MS; ++i) { a[i] = 0.0; a2[i] = 0.0; }
           const uint32_t* wr = St + (size_t)rr * lh;
+          const uint32_t* wr2 = wr + (two ? (size_t)NW * lh : 0);
           for (int w = lane; w < lh; w += 32) {
             const double2 er = widen2(wr[w], wr[pw + w]);  // Re of k = 2w, 2w+1
             const double2 ei = widen2(wr[2 * pw + w], wr[3 * pw + w]);
+            const double2 fr = widen2(wr2[w], wr2[pw + w]);
+            const double2 fi = widen2(wr2[2 * pw + w], wr2[3 * pw + w]);
 #pragma unroll
             for (int j = 0; j < MS; ++j) {
               const cplx x = vc[(size_t)(2 * j) * lh + w], y = vc[(size_t)(2 * j + 1) * lh + w];
@@ -241,12 +251,19 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
               a[2 * j] = fma(er.y, y.x, a[2 * j]); a[2 * j] = fma(-ei.y, y.y, a[2 * j]);
               a[2 * j + 1] = fma(er.x, x.y, a[2 * j + 1]); a[2 * j + 1] = fma(ei.x, x.x, a[2 * j + 1]);
               a[2 * j + 1] = fma(er.y, y.y, a[2 * j + 1]); a[2 * j + 1] = fma(ei.y, y.x, a[2 * j + 1]);
+              if (two) {
+                a2[2 * j] = fma(fr.x, x.x, a2[2 * j]); a2[2 * j] = fma(-fi.x, x.y, a2[2 * j]);
+                a2[2 * j] = fma(fr.y, y.x, a2[2 * j]); a2[2 * j] = fma(-fi.y, y.y, a2[2 * j]);
+                a2[2 * j + 1] = fma(fr.x, x.y, a2[2 * j + 1]); a2[2 * j + 1] = fma(fi.x, x.x, a2[2 * j + 1]);
+                a2[2 * j + 1] = fma(fr.y, y.y, a2[2 * j + 1]); a2[2 * j + 1] = fma(fi.y, y.x, a2[2 * j + 1]);
+              }
             }
           }
           // reduce-scatter: at every step the lower / upper half of the live elements stays with (lane & off) == 0 / != 0,
           // so the element index is read off the lane bits from the top
-          int e;
+          int e, e2 = 0;
           const double v = reduce_scatter<2 * MS>(a, lane, e) * pscale;
+          const double v2 = two ? reduce_scatter<2 * MS>(a2, lane, e2) * pscale : 0.0;
           // after log2(2 MS) halvings the surviving lanes are those with the low (5 - log2(2 MS)) bits arbitrary: let the
           // lane whose low bits are zero write
           constexpr int LOWBITS = 5 - (MS == 8 ? 4 : MS == 4 ? 3 : MS == 2 ? 2 : 1);
@@ -257,6 +274,12 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
               dv[ri] = v;
               double* dp = reinterpret_cast<double*>(&psi_b[(size_t)(step + 1) * mn + (size_t)j * n + row]);
               dp[ri] = v;
+              if (two) {
+                double* dv2 = reinterpret_cast<double*>(&vn[vidx(j, row + NW)]);
+                dv2[ri] = v2;
+                double* dp2 = reinterpret_cast<double*>(&psi_b[(size_t)(step + 1) * mn + (size_t)j * n + row + NW]);
+                dp2[ri] = v2;
+              }
             }
           }
         }

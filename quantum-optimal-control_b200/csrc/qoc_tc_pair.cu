@@ -25,7 +25,7 @@ constexpr int KB_ELEMS = 32;                     // K elements per stage
 constexpr uint32_t A_PLANE_BYTES = 128 * 64;     // box {32 halfs, 128 rows}
 constexpr uint32_t B_PLANE_BYTES = 32 * 128;     // box {64 halfs, 32 rows}: this CTA's half of the tile's columns
 constexpr uint32_t STAGE_BYTES = 4 * A_PLANE_BYTES + 4 * B_PLANE_BYTES;   // 48 KB
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 3;
 constexpr int NEPI = 256;
 constexpr int NHALF = NEPI / 128;
 constexpr int CSTEP = 16 * NHALF;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
                 if (lane == 0 && row0 < n && !(q.tma_store & 2)) tma_store_4d(&smaps.st[dcls], stg, col, row0, 0, (int)(dd == 0 ? o.d1_idx : o.d2_idx));
               }
             }
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this tile's boxes are written, not just read
+            if (lane == 0 && !(q.tma_store & 8)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this tile's boxes are written, not just read
             __syncwarp();
             if (16 * half >= nt) {                     // a warp without any chunk in this tile still owes its arrival
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

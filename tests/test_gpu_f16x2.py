@@ -155,6 +155,27 @@ def test_f16x2_matches_fp64_oracle(name, built_lib):
     eng.close()
 
 
+@pytest.mark.parametrize("name,knob", [('c5_n200_m5', 'QOC_B200_TC_PAIR'), ('c5_n256_m2', 'QOC_B200_TC_PAIR'),
+                                       ('c3_T30', 'QOC_B200_TC_SMALL'), ('c5_n48_m3', 'QOC_B200_TC_SMALL')])
+def test_f16x2_engines_agree_bit_for_bit(name, knob, built_lib, monkeypatch):
+    """The three tcgen05 engines evaluate the same products in the same order (k-blocks ascending, 12 MMAs per 16 columns,
+    fp32 accumulators, the same epilogue arithmetic): the CTA-pair kernel (n > 128) and the shared-memory-resident kernel
+    (n <= 64) must reproduce the streamed-operand engine's propagators BIT FOR BIT, hence identical losses and gradients."""
+    fn, over, B = F16_CASES[name]
+    setups, guess, args, kw = make_case(fn(), seed=11, B=B, **over)
+    res = {}
+    for v in ('1', '0'):
+        monkeypatch.setenv(knob, v)
+        sp, eng = _engine(args, kw, guess, 'f16x2')
+        base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+        out = eng.value_and_grad(base)
+        res[v] = (eng.propagators().clone(), out['loss'].clone(), out['grad'].clone())
+        eng.poll_error()
+        eng.close()
+    assert torch.equal(res['1'][0], res['0'][0])
+    assert torch.equal(res['1'][1], res['0'][1]) and torch.equal(res['1'][2], res['0'][2])
+
+
 def test_f16x2_rejects_what_it_does_not_cover(built_lib):
     from quantum_optimal_control.core.engine import GrapeEngine, QocError
     with pytest.raises(QocError):
