@@ -28,6 +28,21 @@ import os
 # per GPU the ranks share the host's cores and spinning workers would fight each other (measured passive there).
 if int(os.environ.get("WORLD_SIZE", "1")) == 1:
     os.environ.setdefault("OMP_WAIT_POLICY", "ACTIVE")
+elif os.environ.get("QOC_BENCH_PIN", "1") != "0" and hasattr(os, "sched_setaffinity"):
+    # one rank per GPU: give every rank its own slice of the host cores BEFORE any thread pool exists (the pools inherit
+    # the mask), so the ranks' host legs (qoc_adam_host workers, the copy threads) stop migrating onto each other; with
+    # dedicated cores the workers can spin through the GPU wait as in the single-process run
+    try:
+        _cores = sorted(os.sched_getaffinity(0))
+        _lw = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+        _lr = int(os.environ.get("LOCAL_RANK", "0")) % _lw
+        _per = len(_cores) // _lw
+        if _per >= 2:
+            os.sched_setaffinity(0, _cores[_lr * _per:(_lr + 1) * _per])
+            os.environ.setdefault("OMP_WAIT_POLICY", "ACTIVE")
+            os.environ.setdefault("OMP_PROC_BIND", "false")
+    except OSError:
+        pass
 import subprocess
 import sys
 import threading
@@ -295,10 +310,11 @@ def measure(workload, dtype, B, steps, warmup, dev, local, world, rank, steps_T=
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     if e2e:
-        torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))      # host Adam: share the cores between ranks
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else max(1, (os.cpu_count() or 1) // max(world, 1))
+        torch.set_num_threads(max(1, ncores if world > 1 else (os.cpu_count() or 1)))      # host Adam: this rank's cores
         hbase = eng.host_buffers()['base']                      # pinned host weights, updated in place by the host Adam
         hbase[...] = np.asarray(sp.ops_weight_base, dtype=np.float64)
-        hadam = HostAdam(hbase.shape, threads=max(1, min(16 if world == 1 else 4, (os.cpu_count() or 1) // max(world, 1))))
+        hadam = HostAdam(hbase.shape, threads=max(1, min(16 if world == 1 else 4, ncores if world > 1 else (os.cpu_count() or 1))))
         for _ in range(max(1, min(warmup, 5))):
             o = eng.value_and_grad_host(hbase, copy=False)
             hadam.step(hbase, o['grad'], lr)
