@@ -330,6 +330,8 @@ def measure(workload, dtype, B, steps, warmup, dev, local, world, rank, steps_T=
 
     # ---- roofline of the dominant kernel (the propagator stage) ----------------------------------
     ktimes = {k: v * steps / max(sampled, 1) for k, v in ktimes.items()}      # scale the sampled sums to all steps
+    if eng.batch_chunk and eng.batch_chunk < B:      # the per-kernel events of a step cover its LAST workspace-sized pass only
+        ktimes = {k: v * (B / float(eng.batch_chunk)) for k, v in ktimes.items()}
     expm_ms = ktimes['expm'] / steps
     expm_flops = 8.0 * n ** 3 * (p - 1 + s) * T * B                    # (p-1) Taylor products + s squarings per (b,t)
     achieved = expm_flops / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else None
@@ -505,7 +507,7 @@ def run_ours(args):
         # every other BASELINE configuration at its stated size, short runs (device-resident, CUDA events, clocks sampled)
         secondary = {}
         for wl, dt, st, wu in (("C3", "f16x2", 3, 1), ("C3", "f64", 3, 1), ("C4", "f16x2", 2, 1), ("C5n64", "f64", 3, 1),
-                               ("C5n32", "f64", 5, 1), ("C5n16", "f64", 10, 2)):
+                               ("C5n32", "f64", 5, 1), ("C5n16", "f64", 10, 2), ("C5n128", "f64", 1, 1)):
             try:
                 q = measure(wl, dt, None, st, wu, dev, local, 1, 0, e2e=False)
                 rf = q['roofline']
