@@ -331,7 +331,8 @@ def measure(workload, dtype, B, steps, warmup, dev, local, world, rank, steps_T=
     # ---- roofline of the dominant kernel (the propagator stage) ----------------------------------
     ktimes = {k: v * steps / max(sampled, 1) for k, v in ktimes.items()}      # scale the sampled sums to all steps
     if eng.batch_chunk and eng.batch_chunk < B:      # the per-kernel events of a step cover its LAST workspace-sized pass only
-        ktimes = {k: v * (B / float(eng.batch_chunk)) for k, v in ktimes.items()}
+        last = B % eng.batch_chunk or eng.batch_chunk                        # passes: chunk, chunk, ..., remainder
+        ktimes = {k: v * (B / float(last)) for k, v in ktimes.items()}
     expm_ms = ktimes['expm'] / steps
     expm_flops = 8.0 * n ** 3 * (p - 1 + s) * T * B                    # (p-1) Taylor products + s squarings per (b,t)
     achieved = expm_flops / (expm_ms * 1e-3) / 1e12 if expm_ms > 0 else None

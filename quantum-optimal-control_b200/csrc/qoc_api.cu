@@ -621,7 +621,11 @@ int qoc_value_and_grad(qoc_handle_t h, const double* base_dev, double* loss_dev,
     else if (use_vec_sweeps(h, p)) CUDA_TRY(h, qoc_launch_vec_sweep(p, 1, h->d.dtype != QOC_F64, ws, &h->launches));
     else CUDA_TRY(h, qoc_launch_costate(p, h->d.dtype != QOC_F64, ws, &h->launches));
     if ((rc = prof_mark(h, 4, ws))) return rc;
+    // n > 64: the GEMM form pays when the K operators together hold more entries than one n x n matrix per m / 8 states
+    const bool gemm_grad_large = !h->tc && h->d.n > 64 && h->d.dtype == QOC_F64 && qoc_grad_large_supported(p) && !getenv("QOC_B200_NO_GRAD_GEMM") &&
+                                 (double)h->nnz * h->d.m >= 8.0 * (double)h->d.n * h->d.n * 1.5;
     if (dense_m && dense_A) CUDA_TRY(h, qoc_launch_grad_mma(p, h->NP, h->sm_count, ws, &h->launches));
+    else if (gemm_grad_large) CUDA_TRY(h, qoc_launch_grad_large(p, h->sm_count, ws, &h->launches));
     else CUDA_TRY(h, qoc_launch_grad(p, h->sm_count, ws, &h->launches));
     if ((rc = prof_mark(h, 5, ws))) return rc;
     if ((rc = join_hi(h, st))) return rc;                  // finalize reads both branches; the next pass rewrites P

@@ -107,6 +107,8 @@ size_t qoc_large_scratch_elems(int n, int B, int sm_count);
 cudaError_t qoc_launch_expm_large(const QocParams& p, int sm_count, void* scratch, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_chain_large(const QocParams& p, void* scratch, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate_large(const QocParams& p, cudaStream_t st, int64_t* launches);
+bool qoc_grad_large_supported(const QocParams& p);
+cudaError_t qoc_launch_grad_large(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_dress(const QocParams& p, int phase, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_costate_mma(const QocParams& p, int NP, cudaStream_t st, int64_t* launches);
 cudaError_t qoc_launch_grad_mma(const QocParams& p, int NP, int sm_count, cudaStream_t st, int64_t* launches);

@@ -5,6 +5,7 @@
 // squarings (core/tensorflow_state.py:25-46), chain X_t = P_t X_{t-1} (:204-242), costate sweep.
 #include "qoc_internal.cuh"
 #include <math.h>
+#include <algorithm>
 
 #define DEVINL __device__ __forceinline__
 
@@ -344,6 +345,131 @@ __global__ void k_costate_large(QocParams p, int mc) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_grad_large: dense-m, dense-control gradient for n > 64 as ONE GEMM per (b,t) (matexp_op_grad, tensorflow_state.py:49-65):
+//   W[a][c] = sum_j conj(lambda_j(t+1)[a]) psi_j(t+1)[c]   (n x n x m, A = Lambda^H read transposed from its [m][n] storage),
+//   g_k = Re sum_ac A_k[a][c] W[a][c]                        (K dense operators, reduced in the epilogue, W never stored)
+// instead of K n^2 length-m dot products (k_grad): 1/K of the flops, on the DMMA pipe.
+// ---------------------------------------------------------------------------------------------
+constexpr int GRAD_MAXK = 8;
+template <int TS, int RB, int CB>
+__global__ void __launch_bounds__(LT<TS, RB, CB>::THREADS) k_grad_large(QocParams p) {
+  typedef LT<TS, RB, CB> L;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* sm = reinterpret_cast<cplx*>(smem_raw);
+  __shared__ double red[GRAD_MAXK][L::WARPS];
+  const int n = p.n, m = p.m, T = p.T, K = p.K, mn = m * n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int rb0 = (warp / L::WC) * RB, cb0 = (warp % L::WC) * CB;
+  cplx* As = sm;                       // [2][KT*TS]: Lambda tile [j][a] (k-major, like a B tile)
+  cplx* Bs = sm + 2 * L::A_ELEMS;      // [2][KT*TS]: Psi tile [j][c]
+  const int nt = (n + TS - 1) / TS, nk = (m + KT - 1) / KT;
+  const long long items = (long long)p.B * T;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = (int)(item / T), t = (int)(item % T);
+    const size_t off = ((size_t)b * (T + 1) + (t + 1)) * mn;
+    const cplx* __restrict__ lam = p.lam + off;
+    const cplx* __restrict__ psi = p.psi + off;
+    double gk[GRAD_MAXK];
+#pragma unroll
+    for (int k = 0; k < GRAD_MAXK; ++k) gk[k] = 0.0;
+    auto load_tiles = [&](int ti, int tj, int kt, int buf) {
+      cplx* a = As + buf * L::A_ELEMS;
+      cplx* bb = Bs + buf * L::B_ELEMS;
+      for (int idx = tid; idx < KT * TS; idx += L::THREADS) {
+        const int k = idx / TS, c = idx - k * TS;
+        const int gj = kt * KT + k;
+        const int ga = ti * TS + c, gc = tj * TS + c;
+        const bool oka = gj < m && ga < n, okb = gj < m && gc < n;
+        cp_async16_zfill(a + k * TS + (c ^ sw_mask(k)), lam + (oka ? (size_t)gj * n + ga : 0), oka);
+        cp_async16_zfill(bb + k * TS + (c ^ sw_mask(k)), psi + (okb ? (size_t)gj * n + gc : 0), okb);
+      }
+      cp_async_commit();
+    };
+    for (int ti = 0; ti < nt; ++ti)
+      for (int tj = 0; tj < nt; ++tj) {
+        double cr[RB][CB][2], ci[RB][CB][2], t2[RB][CB][2];
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int j = 0; j < CB; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = t2[i][j][0] = t2[i][j][1] = 0.0;
+        __syncthreads();
+        load_tiles(ti, tj, 0, 0);
+        for (int kt = 0; kt < nk; ++kt) {
+          if (kt + 1 < nk) { load_tiles(ti, tj, kt + 1, (kt + 1) & 1); cp_async_wait<1>(); }
+          else cp_async_wait<0>();
+          __syncthreads();
+          const cplx* a = As + (kt & 1) * L::A_ELEMS;
+          const cplx* bb = Bs + (kt & 1) * L::B_ELEMS;
+          const int krem = m - kt * KT;
+          const int ksteps = krem >= KT ? KT / 4 : (krem + 3) / 4;
+#pragma unroll 2
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const int k = 4 * ks + q;
+            const int km = sw_mask(k);
+            cplx av[RB], bv[CB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) { av[i] = a[k * TS + ((8 * (rb0 + i) + g) ^ km)]; av[i].y = -av[i].y; }
+#pragma unroll
+            for (int j = 0; j < CB; ++j) bv[j] = bb[k * TS + ((8 * (cb0 + j) + g) ^ km)];
+            double sa[RB], sb[CB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) sa[i] = av[i].x + av[i].y;
+#pragma unroll
+            for (int j = 0; j < CB; ++j) sb[j] = bv[j].x + bv[j].y;
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+              for (int j = 0; j < CB; ++j) dmma(cr[i][j][0], cr[i][j][1], av[i].x, bv[j].x);
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+              for (int j = 0; j < CB; ++j) dmma(t2[i][j][0], t2[i][j][1], av[i].y, bv[j].y);
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+              for (int j = 0; j < CB; ++j) dmma(ci[i][j][0], ci[i][j][1], sa[i], sb[j]);
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const int r = ti * TS + 8 * (rb0 + i) + g;
+#pragma unroll
+          for (int j = 0; j < CB; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = tj * TS + 8 * (cb0 + j) + 2 * q + e;
+              if (r < n && c < n) {
+                const double vr = cr[i][j][e] - t2[i][j][e], vi = ci[i][j][e] - cr[i][j][e] - t2[i][j][e];
+#pragma unroll
+                for (int k = 0; k < GRAD_MAXK; ++k)
+                  if (k < K) {
+                    const cplx ak = __ldg(p.A + ((size_t)(k + 1) * n + r) * n + c);
+                    gk[k] += ak.x * vr - ak.y * vi;
+                  }
+              }
+            }
+        }
+      }
+#pragma unroll
+    for (int k = 0; k < GRAD_MAXK; ++k)
+      if (k < K) {
+        const double v = warp_sum_d(gk[k]);
+        if (lane == 0) red[k][warp] = v;
+      }
+    __syncthreads();
+    if (tid < K) {
+      double v = 0.0;
+      for (int w = 0; w < L::WARPS; ++w) v += red[tid][w];
+      p.gctrl[((size_t)b * K + tid) * T + t] = v;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 // scratch sizes (complex elements) -----------------------------------------------------------------
@@ -404,5 +530,31 @@ cudaError_t qoc_launch_costate_large(const QocParams& p, cudaStream_t st, int64_
   if (e != cudaSuccess) return e;
   const dim3 grid(p.B, (p.m + mc - 1) / mc);
   k_costate_large<<<grid, 256, smem, st>>>(p, mc);
+  return cudaGetLastError();
+}
+
+bool qoc_grad_large_supported(const QocParams& p) { return p.n > 64 && p.K <= GRAD_MAXK; }
+
+cudaError_t qoc_launch_grad_large(const QocParams& p, int sm_count, cudaStream_t st, int64_t* launches) {
+  ++*launches;
+  const long long items = (long long)p.B * p.T;
+  cudaError_t e;
+  if (pick_ts(p.n) == 72) {
+    typedef LT<72, 3, 3> L;
+    e = cudaFuncSetAttribute(k_grad_large<72, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_grad_large<72, 3, 3>, L::THREADS, L::SMEM);
+    const long long grid = std::min<long long>(items, (long long)sm_count * (occ < 1 ? 1 : occ));
+    k_grad_large<72, 3, 3><<<(unsigned)grid, L::THREADS, L::SMEM, st>>>(p);
+  } else {
+    typedef LT<64, 2, 4> L;
+    e = cudaFuncSetAttribute(k_grad_large<64, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_grad_large<64, 2, 4>, L::THREADS, L::SMEM);
+    const long long grid = std::min<long long>(items, (long long)sm_count * (occ < 1 ? 1 : occ));
+    k_grad_large<64, 2, 4><<<(unsigned)grid, L::THREADS, L::SMEM, st>>>(p);
+  }
   return cudaGetLastError();
 }
