@@ -25,6 +25,7 @@
 #include "qoc_tc_dev.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -32,7 +33,7 @@ constexpr int S_MAXWPQ = 3;                      // epilogue warps per TMEM lane
 constexpr uint32_t GUARD_BYTES = 8 * 1024;       // readable finite bytes before the first image (slot 0 starts pad <= 63 rows early)
 constexpr uint32_t TAIL_GUARD_BYTES = 4 * 1024;  // ... and after the last one (its 128-row window overshoots by < 2 KB)
 
-struct SmallGeom { int n, N16, K16, RP, NSL, QPS, WPQ, DIOFF, pad; uint32_t plane_bytes, mat_bytes, slot_bytes; size_t smem; int tmem_cols; };
+struct SmallGeom { int n, N16, K16, RP, NSL, QPS, WPQ, DIOFF, pad, wide; uint32_t plane_bytes, mat_bytes, slot_bytes; size_t smem; int tmem_cols; };
 
 __host__ __device__ inline bool small_geometry(int n, SmallGeom& g) {
   if (n < 1 || n > 64) return false;
@@ -50,6 +51,12 @@ __host__ __device__ inline bool small_geometry(int n, SmallGeom& g) {
   g.mat_bytes = 4 * g.plane_bytes;
   g.slot_bytes = 3 * g.mat_bytes;                // X, Y, Z
   g.smem = (size_t)GUARD_BYTES + TAIL_GUARD_BYTES + (size_t)g.NSL * g.slot_bytes + 1024;
+  // two slots (32 < n <= 64): "wide" products.  The Re and Im planes of the B operand are two 64-column swizzle atoms
+  // 2 plane_bytes apart, so ONE N = 128 MMA multiplies an A plane with [Br | Bi]: D1 = Ar [Br | Bi], D2 = Ai [Br | Bi],
+  // Dr = D1[0:64) - D2[64:128), Di = D1[64:128) + D2[0:64) in the epilogue -- 18 instead of 36 MMAs per product (the
+  // kernel is bound by the ~45 issue cycles of each tcgen05.mma, not by their width)
+  g.wide = g.NSL == 2 ? 1 : 0;
+  if (g.wide) g.DIOFF = 128;
   int cols = 32;
   while (cols < g.NSL * 2 * g.DIOFF) cols *= 2;
   g.tmem_cols = cols;
@@ -151,6 +158,24 @@ __global__ void __launch_bounds__(448, 1) k_tc_small_expm(const TcParams q, cons
             da[pl] = make_desc(abase + pl * g.plane_bytes, 1, 1024 >> 4, 2);          // K-major SWIZZLE_128B
             db[pl] = make_desc(bbase + pl * g.plane_bytes, 1, 1024 >> 4, 2);          // MN-major SWIZZLE_128B
           }
+          if (g.wide) {
+            const uint32_t idw = (1u << 4) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // N = 128: [Re atom | Im atom]
+            uint64_t dw[2];
+            dw[0] = make_desc(bbase, (2 * g.plane_bytes) >> 4, 1024 >> 4, 2);                     // [Br h0 | Bi h0]
+            dw[1] = make_desc(bbase + g.plane_bytes, (2 * g.plane_bytes) >> 4, 1024 >> 4, 2);     // [Br h1 | Bi h1]
+            for (int k = 0; k < g.K16; ++k) {
+              const uint32_t first = k == 0 ? 0u : 1u;
+              mma_f16_ss(dr, da[0], dw[1], idw, first);        // D1 += Ar0 [B1]
+              mma_f16_ss(di, da[2], dw[1], idw, first);        // D2 += Ai0 [B1]
+              mma_f16_ss(dr, da[1], dw[0], idw, 1u);           // D1 += Ar1 [B0]
+              mma_f16_ss(di, da[3], dw[0], idw, 1u);           // D2 += Ai1 [B0]
+              mma_f16_ss(dr, da[0], dw[0], idw, 1u);           // D1 += Ar0 [B0]
+              mma_f16_ss(di, da[2], dw[0], idw, 1u);           // D2 += Ai0 [B0]
+#pragma unroll
+              for (int pl = 0; pl < 4; ++pl) da[pl] += 32 >> 4;
+              dw[0] += 2048 >> 4; dw[1] += 2048 >> 4;
+            }
+          } else
           for (int k = 0; k < g.K16; ++k) {
             const uint32_t first = k == 0 ? 0u : 1u;
             // Dr and Di alternate (independent accumulation chains)
@@ -249,9 +274,23 @@ __global__ void __launch_bounds__(448, 1) k_tc_small_expm(const TcParams q, cons
         auto dst_of = [&](int d) -> uint32_t { return d == 1 ? imgY : imgZ; };
         for (int c0 = 16 * cg; c0 < N16; c0 += 16 * WPQ) {
           uint32_t ur[16], ui[16];
-          tmem_ld16(lane_addr + (uint32_t)c0, ur);
-          tmem_ld16(lane_addr + (uint32_t)(g.DIOFF + c0), ui);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (g.wide) {                              // Dr = D1[c0] - D2[64 + c0], Di = D1[64 + c0] + D2[c0]
+            uint32_t t1[16], t2[16];
+            tmem_ld16(lane_addr + (uint32_t)c0, ur);
+            tmem_ld16(lane_addr + (uint32_t)(128 + 64 + c0), t1);
+            tmem_ld16(lane_addr + (uint32_t)(64 + c0), ui);
+            tmem_ld16(lane_addr + (uint32_t)(128 + c0), t2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              ur[i] = __float_as_uint(__uint_as_float(ur[i]) - __uint_as_float(t1[i]));
+              ui[i] = __float_as_uint(__uint_as_float(ui[i]) + __uint_as_float(t2[i]));
+            }
+          } else {
+            tmem_ld16(lane_addr + (uint32_t)c0, ur);
+            tmem_ld16(lane_addr + (uint32_t)(g.DIOFF + c0), ui);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
           if (prof) { const long long c = clock64(); tp[2] += c - c0p; c0p = c; }
           if (!(valid && vrow)) continue;
 #pragma unroll
@@ -313,6 +352,12 @@ bool tc_small_supported(int n) {
 cudaError_t tc_small_launch_expm(const TcParams& q, int n, int sm_count, cudaStream_t st) {
   SmallGeom g;
   if (!small_geometry(n, g)) return cudaErrorNotSupported;
+  if (g.wide && getenv("QOC_B200_SMALL_WIDE") && atoi(getenv("QOC_B200_SMALL_WIDE")) == 0) {   // A/B knob: 36 narrow MMAs per product
+    g.wide = 0; g.DIOFF = (g.N16 + 31) / 32 * 32;
+    int cols = 32;
+    while (cols < g.NSL * 2 * g.DIOFF) cols *= 2;
+    g.tmem_cols = cols;
+  }
   cudaError_t e = cudaFuncSetAttribute(k_tc_small_expm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
   long long groups = (q.items + g.NSL - 1) / g.NSL;

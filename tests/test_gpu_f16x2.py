@@ -156,13 +156,16 @@ def test_f16x2_matches_fp64_oracle(name, built_lib):
 
 
 @pytest.mark.parametrize("name,knob", [('c5_n200_m5', 'QOC_B200_TC_PAIR'), ('c5_n256_m2', 'QOC_B200_TC_PAIR'),
-                                       ('c3_T30', 'QOC_B200_TC_SMALL'), ('c5_n48_m3', 'QOC_B200_TC_SMALL')])
+                                       ('c3_T30', 'QOC_B200_TC_SMALL'), ('c5_n48_m3', 'QOC_B200_TC_SMALL'),
+                                       ('c2_T40', 'QOC_B200_TC_SMALL')])
 def test_f16x2_engines_agree_bit_for_bit(name, knob, built_lib, monkeypatch):
     """The three tcgen05 engines evaluate the same products in the same order (k-blocks ascending, 12 MMAs per 16 columns,
     fp32 accumulators, the same epilogue arithmetic): the CTA-pair kernel (n > 128) and the shared-memory-resident kernel
-    (n <= 64) must reproduce the streamed-operand engine's propagators BIT FOR BIT, hence identical losses and gradients."""
+    (n <= 64, with its narrow products: QOC_B200_SMALL_WIDE=0) must reproduce the streamed-operand engine's propagators
+    BIT FOR BIT, hence identical losses and gradients."""
     fn, over, B = F16_CASES[name]
     setups, guess, args, kw = make_case(fn(), seed=11, B=B, **over)
+    monkeypatch.setenv('QOC_B200_SMALL_WIDE', '0')
     res = {}
     for v in ('1', '0'):
         monkeypatch.setenv(knob, v)
@@ -174,6 +177,26 @@ def test_f16x2_engines_agree_bit_for_bit(name, knob, built_lib, monkeypatch):
         eng.close()
     assert torch.equal(res['1'][0], res['0'][0])
     assert torch.equal(res['1'][1], res['0'][1]) and torch.equal(res['1'][2], res['0'][2])
+
+
+@pytest.mark.parametrize("name", ['c3_T30', 'c5_n48_m3'])
+def test_f16x2_wide_products_match_narrow_ones(name, built_lib, monkeypatch):
+    """32 < n <= 64: the N = 128 products (D1 = Ar [Br | Bi], D2 = Ai [Br | Bi], combined in the epilogue) against the
+    12-MMA form: the same fp16-pair terms, two fp32 accumulators instead of one per component -> equal to fp32 rounding."""
+    fn, over, B = F16_CASES[name]
+    setups, guess, args, kw = make_case(fn(), seed=11, B=B, **over)
+    res = {}
+    for v in ('1', '0'):
+        monkeypatch.setenv('QOC_B200_SMALL_WIDE', v)
+        sp, eng = _engine(args, kw, guess, 'f16x2')
+        base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+        out = eng.value_and_grad(base)
+        res[v] = (eng.propagators().clone(), out['loss'].clone(), out['grad'].clone())
+        eng.poll_error()
+        eng.close()
+    assert (res['1'][0] - res['0'][0]).abs().max().item() < 1e-6
+    assert (res['1'][1] - res['0'][1]).abs().max().item() < 1e-6
+    assert (res['1'][2] - res['0'][2]).abs().max().item() < 1e-5 * res['0'][2].abs().max().item()
 
 
 def test_f16x2_rejects_what_it_does_not_cover(built_lib):
