@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(448, 1) k_tc_small_expm(const TcParams q, cons
     // the last product (a squaring whenever s >= 1) does not touch X: the next round's generator is assembled while the
     // tensor pipe works on it
     const TcExpmOp elast = ops_s[nops - 1];
-    const bool early_x = NSL == 4 && nops >= 2 && elast.sa != 0 && elast.sb != 0 && (elast.se != 0 || (elast.c1[1] == 0.f && elast.c2[1] == 0.f));
+    const bool early_x = nops >= 2 && elast.sa != 0 && elast.sb != 0 && (elast.se != 0 || (elast.c1[1] == 0.f && elast.c2[1] == 0.f));
     for (int round = 0; round < nrounds_total && ok; ++round) {
       const long long item = ((long long)round * gridDim.x + blockIdx.x) * NSL + s;
       const bool valid = item < q.items;
