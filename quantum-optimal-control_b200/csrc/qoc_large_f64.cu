@@ -5,6 +5,7 @@
 // squarings (core/tensorflow_state.py:25-46), chain X_t = P_t X_{t-1} (:204-242), costate sweep.
 #include "qoc_internal.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 #define DEVINL __device__ __forceinline__
@@ -47,16 +48,18 @@ struct LT {
 };
 
 // C (n x n, ldc) = A (lda) * B (ldb)  [+ c_id * I + c_h * Hadd]   -- one CTA, all operands in global memory
-template <int TS, int RB, int CB>
+// mrows < n: A and C have only mrows rows (dense-m costate: Lambda is [m][n]); CONJB: B is used conjugated
+template <int TS, int RB, int CB, bool CONJB = false>
 DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict__ B, int ldb, cplx* __restrict__ C, int ldc,
-                     int n, double c_id, double c_h, const cplx* __restrict__ Hadd, int ldh, cplx* sm) {
+                     int n, double c_id, double c_h, const cplx* Hadd, int ldh, cplx* sm, int mrows = -1) {
+  if (mrows < 0) mrows = n;
   typedef LT<TS, RB, CB> L;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int rb0 = (warp / L::WC) * RB, cb0 = (warp % L::WC) * CB;
   cplx* As = sm;                       // [2][TS*KT]
   cplx* Bs = sm + 2 * L::A_ELEMS;      // [2][KT*TS]
-  const int nt = (n + TS - 1) / TS, nk = (n + KT - 1) / KT;
+  const int nt = (n + TS - 1) / TS, nk = (n + KT - 1) / KT, ntr = (mrows + TS - 1) / TS;
 
   auto load_tiles = [&](int ti, int tj, int kt, int buf) {
     cplx* a = As + buf * L::A_ELEMS;
@@ -64,7 +67,7 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
     for (int idx = tid; idx < TS * KT; idx += L::THREADS) {
       const int r = idx / KT, k = idx - r * KT;
       const int gr = ti * TS + r, gk = kt * KT + k;
-      const bool ok = gr < n && gk < n;
+      const bool ok = gr < mrows && gk < n;
       cp_async16_zfill(a + r * KT + (k ^ sw_mask(r)), A + (ok ? (size_t)gr * lda + gk : 0), ok);
     }
     for (int idx = tid; idx < KT * TS; idx += L::THREADS) {
@@ -76,7 +79,7 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
     cp_async_commit();
   };
 
-  for (int ti = 0; ti < nt; ++ti)
+  for (int ti = 0; ti < ntr; ++ti)
     for (int tj = 0; tj < nt; ++tj) {
       // 3M (Gauss) complex product, as in qoc_mma_f64.cu: cr = Ar Br, t2 = Ai Bi, ci = (Ar+Ai)(Br+Bi); combined below
       double cr[RB][CB][2], ci[RB][CB][2], t2[RB][CB][2];
@@ -102,7 +105,7 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
           for (int i = 0; i < RB; ++i) { const int r = 8 * (rb0 + i) + g; av[i] = a[r * KT + (k ^ sw_mask(r))]; }
           const int bm = sw_mask(k);
 #pragma unroll
-          for (int j = 0; j < CB; ++j) bv[j] = b[k * TS + ((8 * (cb0 + j) + g) ^ bm)];
+          for (int j = 0; j < CB; ++j) { bv[j] = b[k * TS + ((8 * (cb0 + j) + g) ^ bm)]; if (CONJB) bv[j].y = -bv[j].y; }
           double sa[RB], sb[CB];
 #pragma unroll
           for (int i = 0; i < RB; ++i) sa[i] = av[i].x + av[i].y;
@@ -131,7 +134,7 @@ DEVINL void cta_gemm(const cplx* __restrict__ A, int lda, const cplx* __restrict
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int c = tj * TS + 8 * (cb0 + j) + 2 * q + e;
-            if (r < n && c < n) {
+            if (r < mrows && c < n) {
               double vr = cr[i][j][e] - t2[i][j][e], vi = ci[i][j][e] - cr[i][j][e] - t2[i][j][e];
               if (Hadd) { const cplx h = Hadd[(size_t)r * ldh + c]; vr += c_h * h.x; vi += c_h * h.y; }
               if (r == c) vr += c_id;
@@ -347,6 +350,67 @@ __global__ void k_costate_large(QocParams p, int mc) {
 
 
 // ---------------------------------------------------------------------------------------------
+// k_costate_large_mma: dense-m reverse sweep for n > 64 on the DMMA tiles.  With the states as rows,
+//   L(t) = L(t+1) conj(P_t) + S(t),   L = [m][n]  (lambda_j(t) = P_t^dagger lambda_j(t+1) + s_j(t), tensorflow_state.py:214-220 reversed)
+// is one m x n x n GEMM per step; one CTA per instance walks t = T-1 .. 1 (the scalar k_costate_large needs n dependent
+// FMAs per element and step).  Sources are written into L(t) first and added by the GEMM epilogue.
+// ---------------------------------------------------------------------------------------------
+template <int TS, int RB, int CB>
+__global__ void __launch_bounds__(LT<TS, RB, CB>::THREADS) k_costate_large_mma(QocParams p) {
+  typedef LT<TS, RB, CB> L;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* sm = reinterpret_cast<cplx*>(smem_raw);
+  const int n = p.n, m = p.m, T = p.T, mn = m * n;
+  const size_t nn = (size_t)n * n;
+  const int tid = threadIdx.x, nth = L::THREADS;
+  const int b = blockIdx.x;
+  const cplx* Pg = reinterpret_cast<const cplx*>(p.P) + (size_t)b * T * nn;
+  const cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
+  cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn;
+  const double* sc = p.scal + (size_t)b * 8;
+  const double o_re = sc[0], o_im = sc[1], spdfac = sc[4];
+  const bool forb = p.reg.has_forbidden && p.fw != nullptr;
+  const bool spd = p.reg.has_speed_up != 0;
+  const bool has_src = forb || spd;
+  const double m2 = (double)m * (double)m;
+  auto source = [&](int t, int idx) -> cplx {
+    cplx s = make_double2(0.0, 0.0);
+    if (forb && p.dressW) {
+      const cplx d = p.psid[((size_t)b * (T + 1) + t) * mn + idx];
+      s.x += d.x; s.y += d.y;
+    } else if (forb) {
+      const cplx x = psi_b[(size_t)t * mn + idx];
+      const double pop = x.x * x.x + x.y * x.y;
+      const double c = p.fw[idx % n] / (double)T * 2.0 * pop;
+      s.x += c * x.x; s.y += c * x.y;
+    }
+    if (spd) {
+      const cplx o = p.ot[(size_t)b * (T + 1) + t];
+      const cplx ph = p.phi[idx];
+      s.x += spdfac * (o.x * ph.x - o.y * ph.y); s.y += spdfac * (o.x * ph.y + o.y * ph.x);
+    }
+    return s;
+  };
+  for (int idx = tid; idx < mn; idx += nth) {
+    const cplx ph = p.phi[idx];
+    cplx l = make_double2((o_re * ph.x - o_im * ph.y) * (-2.0 / m2), (o_re * ph.y + o_im * ph.x) * (-2.0 / m2));
+    const cplx s = source(T, idx);
+    l.x += s.x; l.y += s.y;
+    lam_b[(size_t)T * mn + idx] = l;
+  }
+  __syncthreads();
+  for (int t = T - 1; t >= 1; --t) {
+    cplx* Lt = lam_b + (size_t)t * mn;
+    if (has_src) {
+      for (int idx = tid; idx < mn; idx += nth) Lt[idx] = source(t, idx);
+      __syncthreads();
+    }
+    cta_gemm<TS, RB, CB, true>(lam_b + (size_t)(t + 1) * mn, n, Pg + (size_t)t * nn, n, Lt, n, n, 0.0, has_src ? 1.0 : 0.0,
+                               has_src ? Lt : nullptr, n, sm, m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_grad_large: dense-m, dense-control gradient for n > 64 as ONE GEMM per (b,t) (matexp_op_grad, tensorflow_state.py:49-65):
 //   W[a][c] = sum_j conj(lambda_j(t+1)[a]) psi_j(t+1)[c]   (n x n x m, A = Lambda^H read transposed from its [m][n] storage),
 //   g_k = Re sum_ac A_k[a][c] W[a][c]                        (K dense operators, reduced in the epilogue, W never stored)
@@ -522,6 +586,21 @@ cudaError_t qoc_launch_chain_large(const QocParams& p, void* scratch, cudaStream
 
 cudaError_t qoc_launch_costate_large(const QocParams& p, cudaStream_t st, int64_t* launches) {
   ++*launches;
+  if (2 * p.m >= 64 && !getenv("QOC_B200_NO_COSTATE_GEMM")) {            // dense-m: one GEMM per step on the DMMA tiles
+    cudaError_t e;
+    if (pick_ts(p.n) == 72) {
+      typedef LT<72, 3, 3> L;
+      e = cudaFuncSetAttribute(k_costate_large_mma<72, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+      if (e != cudaSuccess) return e;
+      k_costate_large_mma<72, 3, 3><<<p.B, L::THREADS, L::SMEM, st>>>(p);
+    } else {
+      typedef LT<64, 2, 4> L;
+      e = cudaFuncSetAttribute(k_costate_large_mma<64, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+      if (e != cudaSuccess) return e;
+      k_costate_large_mma<64, 2, 4><<<p.B, L::THREADS, L::SMEM, st>>>(p);
+    }
+    return cudaGetLastError();
+  }
   int mc = p.m;
   while ((size_t)2 * mc * p.n * sizeof(cplx) > 96 * 1024 && mc > 1) mc = (mc + 1) / 2;
   if (mc > 4) mc = 4;                                   // more CTAs: the sweep is latency bound

@@ -34,6 +34,8 @@ CASES = {
     'c5_n50': (lambda: W.c5_random(50, T=5), {}, 1),
     'c5_n64': (lambda: W.c5_random(64, T=5), {}, 1),
     'c5_n72': (lambda: W.c5_random(72, T=3), {}, 1),
+    # dense m and dense controls above n = 64: GEMM-form gradient (k_grad_large) and costate chain (k_costate_large_mma) with sources
+    'c5_n80_dense_regs': (lambda: W.c5_random(80, T=6), dict(reg_coeffs={'dwdt': 0.1, 'speed_up': 0.3, 'forbidden_coeff_list': [2.0, 1.0], 'states_forbidden_list': [7, 50]}), 2),
     'c5_n100_regs': (lambda: W.c5_random(100, T=3), dict(states_concerned_list=[0, 5, 99], reg_coeffs={'dwdt': 0.1, 'forbidden_coeff_list': [2.0], 'states_forbidden_list': [7]}), 2),
     'c5_n128': (lambda: W.c5_random(128, T=2), dict(states_concerned_list=list(range(8))), 1),
     'c4_T4': (lambda: W.c4_three_transmon_toffoli(T=4), dict(total_time=0.2), 1),
