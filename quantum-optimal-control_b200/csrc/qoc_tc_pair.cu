@@ -409,9 +409,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
                 if (dcls < 0) continue;
                 const bool final_dst = dd == 1 || o.d2_cls < 0;            // ur / ui / e0 are dead after this destination
                 const float k0 = dd == 0 ? o.c1[0] : o.c2[0], k1 = dd == 0 ? o.c1[1] : o.c2[1], k2 = dd == 0 ? o.c1[2] : o.c2[2];
-                uint32_t pk[4][8];                     // plane-set words of this thread's 16 columns
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has left the staging
+                __syncwarp();
+                const uint32_t sw = (uint32_t)((lane >> 2) & 1) << 4;
 #pragma unroll
-                for (int comp = 0; comp < 2; ++comp) {
+                for (int comp = 0; comp < 2; ++comp) {       // one component at a time: half the live registers
                   float ov[16];
                   if (useE) {
                     float ee[16];
@@ -427,24 +429,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
 #pragma unroll
                     for (int i = 0; i < 16; ++i) if (i == dc) ov[i] += k2;
                   }
+                  uint32_t p0[8], p1[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) split2(ov[2 * i], ov[2 * i + 1], pk[2 * comp][i], pk[2 * comp + 1][i]);
+                  for (int i = 0; i < 8; ++i) split2(ov[2 * i], ov[2 * i + 1], p0[i], p1[i]);
+                  const uint32_t b0 = stg + (uint32_t)(2 * comp) * 1024u + (uint32_t)lane * 32u, b1 = b0 + 1024u;
+                  sts128(b0 + sw, p0[0], p0[1], p0[2], p0[3]); sts128(b0 + (16u ^ sw), p0[4], p0[5], p0[6], p0[7]);
+                  sts128(b1 + sw, p1[0], p1[1], p1[2], p1[3]); sts128(b1 + (16u ^ sw), p1[4], p1[5], p1[6], p1[7]);
                 }
                 if (final_dst && !last) {
                   if (useE) fetchE(c0 + CSTEP);
                   tmem_ld16(lane_addr + (uint32_t)(c0 + CSTEP), ur);
                   tmem_ld16(lane_addr + (uint32_t)(128 + c0 + CSTEP), ui);
-                }
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has left the staging
-                __syncwarp();
-                {
-                  const uint32_t sw = (uint32_t)((lane >> 2) & 1) << 4;
-#pragma unroll
-                  for (int pl = 0; pl < 4; ++pl) {
-                    const uint32_t b0 = stg + (uint32_t)pl * 1024u + (uint32_t)lane * 32u;
-                    sts128(b0 + sw, pk[pl][0], pk[pl][1], pk[pl][2], pk[pl][3]);
-                    sts128(b0 + (16u ^ sw), pk[pl][4], pk[pl][5], pk[pl][6], pk[pl][7]);
-                  }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
