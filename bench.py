@@ -504,6 +504,26 @@ def run_ours(args):
                      "best_instance": int(torch.argmin(allv).item())}
 
     secondary = None
+    if world > 1 and not args.no_secondary and args.workload == "C2" and args.steps_T is None and args.batch is None:
+        # BASELINE configs[4] through the multi-GPU launch: the Hilbert-dimension sweep, 512 instances per GPU (4096 over 8 GPUs),
+        # every rank runs its shard, the time is the max over ranks (no collective in the iteration)
+        secondary = {}
+        for wl, dt, st, wu in (("C5n16", "f64", 10, 2), ("C5n32", "f64", 5, 1), ("C5n64", "f64", 3, 1), ("C5n128", "f64", 1, 1)):
+            key = "%s/%s" % (wl, dt)
+            try:
+                q = measure(wl, dt, None, st, wu, dev, local, world, rank, e2e=False, want_peak=False)
+                t = torch.tensor([q['ms']], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_max = float(t.item())
+                secondary[key] = {
+                    "workload": "%s: n=%d K=%d T=%d m=%d, B=%d per GPU x %d GPUs, (p,s)=(%d,%d), %s" % (wl, q['n'], q['K'], q['T'], q['m'], q['B'], world, q['p'], q['s'], dt),
+                    "ms_per_step": ms_max / st, "value": world * q['B'] * st / (ms_max * 1e-3), "unit": UNIT, "steps": st, "warmup": wu,
+                    "n_gpus": world, "batch_chunk": q['batch_chunk'], "clocks": q['clocks'], "gpu_launches": q['launches'],
+                    "kernel_ms_per_step": q['roofline']["kernel_ms_per_step"]}
+            except Exception as e:  # noqa: BLE001
+                secondary[key] = {"error": repr(e)[:300]}
+        if rank != 0:
+            secondary = None
     if rank == 0 and world == 1 and not args.no_secondary and args.workload == "C2" and args.steps_T is None and args.batch is None:
         # every other BASELINE configuration at its stated size, short runs (device-resident, CUDA events, clocks sampled)
         secondary = {}
