@@ -508,7 +508,8 @@ def run_ours(args):
         # BASELINE configs[4] through the multi-GPU launch: the Hilbert-dimension sweep, 512 instances per GPU (4096 over 8 GPUs),
         # every rank runs its shard, the time is the max over ranks (no collective in the iteration)
         secondary = {}
-        for wl, dt, st, wu in (("C5n16", "f64", 10, 2), ("C5n32", "f64", 5, 1), ("C5n64", "f64", 3, 1), ("C5n128", "f64", 1, 1)):
+        for wl, dt, st, wu in (("C5n8", "f64", 10, 2), ("C5n16", "f64", 10, 2), ("C5n32", "f64", 5, 1), ("C5n64", "f64", 3, 1),
+                               ("C5n128", "f64", 1, 1)):
             key = "%s/%s" % (wl, dt)
             try:
                 q = measure(wl, dt, None, st, wu, dev, local, world, rank, e2e=False, want_peak=False)
@@ -528,7 +529,7 @@ def run_ours(args):
         # every other BASELINE configuration at its stated size, short runs (device-resident, CUDA events, clocks sampled)
         secondary = {}
         for wl, dt, st, wu in (("C3", "f16x2", 3, 1), ("C3", "f64", 3, 1), ("C4", "f16x2", 2, 1), ("C5n64", "f64", 3, 1),
-                               ("C5n32", "f64", 5, 1), ("C5n16", "f64", 10, 2), ("C5n128", "f64", 1, 1)):
+                               ("C5n32", "f64", 5, 1), ("C5n16", "f64", 10, 2), ("C5n8", "f64", 10, 2), ("C5n128", "f64", 1, 1)):
             try:
                 q = measure(wl, dt, None, st, wu, dev, local, 1, 0, e2e=False)
                 rf = q['roofline']
