@@ -460,6 +460,8 @@ static int tc_prepare(qoc_handle_t h, cudaStream_t st) {
   tc_pack_host(h->U0_host, d.n, g.ld, TC_EU, hbuf.data());
   tc_pack_host(I.data(), d.n, g.ld, TC_EU, hbuf.data() + g.mat_halfs);
   CUDA_TRY(h, cudaMemcpyAsync(h->tc_const, hbuf.data(), hbuf.size() * sizeof(__half), cudaMemcpyHostToDevice, st));
+  // the generator slots of the scratch are only ever written on the union sparsity pattern of the A_k: zero everything once
+  CUDA_TRY(h, cudaMemsetAsync(h->tc_scr, 0, (size_t)h->tc_grid * QOC_TC_ILV * TC_NSLOT * g.mat_halfs * sizeof(__half), st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
   const void* base[TC_NCLS] = {h->tc_scr, h->P, h->tc_seg, h->tc_const};
   const unsigned long long cnt[TC_NCLS] = {(unsigned long long)h->tc_grid * QOC_TC_ILV * TC_NSLOT, (unsigned long long)h->Bc * d.T,
@@ -487,6 +489,7 @@ static int tc_launch_expm(qoc_handle_t h, const QocParams& p, cudaStream_t st) {
   q.ilv = p.n > 128 ? 1 : QOC_TC_ILV;               // n > 128: four tiles per product already decouple MMA and epilogue, and one
                                                     // item per CTA keeps the scratch working set (148 x 1.5 MB) near the L2 size
   q.nops = h->tc_nops; q.ops = h->tc_ops; q.K = p.K; q.T = p.T; q.ctrl = p.base; q.maxA = p.maxA; q.A_f = h->A_f; q.xscale = h->tc_xscale;
+  if (!getenv("QOC_B200_TC_DENSE_X")) { q.pat_n = h->pat_n; q.pat_rc = h->pat_rc; q.pat_coef_f = h->pat_coef_f; }   // sparse generators: scatter the pattern
   ++h->launches;
   const int small_on = getenv("QOC_B200_TC_SMALL") ? atoi(getenv("QOC_B200_TC_SMALL")) : 1;     // read per call: tests flip it
   if (small_on && tc_small_supported(p.n)) {       // n <= 64: operands resident in shared memory (qoc_tc_small.cu)

@@ -140,6 +140,23 @@ DEVINL void store_comp16(__half* p0, size_t plane, const float (&v)[16]) {
   stg256(p0, a0);
   stg256(p0 + plane, a1);
 }
+// one real -> its fp16 pair
+DEVINL void split1(float a, unsigned short& h0, unsigned short& h1) {
+  const __half x = __float2half_rn(a);
+  const __half y = __float2half_rn(a - __half2float(x));
+  h0 = __half_as_ushort(x); h1 = __half_as_ushort(y);
+}
+// sparse generator assembly (global plane sets): entry e of the union pattern, x = sum_k w_k coef[e][k]
+DEVINL void scatter_x_entry(const TcParams& q, __half* X, size_t plane, int ld, int e, const float* wts) {
+  const int rc = __ldg(q.pat_rc + e), pr = rc >> 16, pc = rc & 0xffff;
+  const float2* cf = q.pat_coef_f + (size_t)e * (q.K + 1);
+  float xr = 0.f, xi = 0.f;
+  for (int k = 0; k <= q.K; ++k) { const float2 a = __ldg(cf + k); xr = fmaf(wts[k], a.x, xr); xi = fmaf(wts[k], a.y, xi); }
+  unsigned short r0, r1, i0, i1;
+  split1(xr, r0, r1); split1(xi, i0, i1);
+  unsigned short* o = reinterpret_cast<unsigned short*>(X) + (size_t)pr * ld + pc;
+  o[0] = r0; o[plane] = r1; o[2 * plane] = i0; o[3 * plane] = i1;
+}
 DEVINL void unpack16(const uint32_t (&h0)[8], const uint32_t (&h1)[8], float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {

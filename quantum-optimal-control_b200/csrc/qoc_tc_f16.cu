@@ -96,15 +96,15 @@ DEVINL void make_op(const TcParams& q, long long item, int j, int nops, int z, i
         o.a_cls = TC_CLS_P; o.a_idx = pb + t0; o.b_cls = TC_CLS_CONST; o.b_idx = 1;
       } else {
         o.a_cls = TC_CLS_P; o.a_idx = pb + t0 + j + 1;
-        if (j == 0) { o.b_cls = TC_CLS_P; o.b_idx = pb + t0; } else { o.b_cls = TC_CLS_SCR; o.b_idx = sb + ((j - 1) & 1); }
+        if (j == 0) { o.b_cls = TC_CLS_P; o.b_idx = pb + t0; } else { o.b_cls = TC_CLS_SCR; o.b_idx = sb + 2 + ((j - 1) & 1); }   // slots 2, 3: 0 and 4 hold generators
       }
-      if (j == nops - 1) { o.d1_cls = TC_CLS_SEG; o.d1_idx = item; } else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + (j & 1); }
+      if (j == nops - 1) { o.d1_cls = TC_CLS_SEG; o.d1_idx = item; } else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + 2 + (j & 1); }
       break;
     }
     case TC_PROG_CHAIN: {
       o.a_cls = q.chain_cls; o.a_idx = item * q.chain_len + j;
-      if (j == 0) { o.b_cls = TC_CLS_CONST; o.b_idx = 0; } else { o.b_cls = TC_CLS_SCR; o.b_idx = sb + ((j - 1) & 1); }
-      if (j == nops - 1) o.f64out = 1; else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + (j & 1); }
+      if (j == 0) { o.b_cls = TC_CLS_CONST; o.b_idx = 0; } else { o.b_cls = TC_CLS_SCR; o.b_idx = sb + 2 + ((j - 1) & 1); }
+      if (j == nops - 1) o.f64out = 1; else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + 2 + (j & 1); }
       break;
     }
     default: {
@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
       const int nops = item_nops(q, it0);
       // generators of one round: X' = xscale (A_0 + sum_k u_k A_k), u_k = maxA_k sin(base[b][k][t])  (init_tf_ops_weight,
       // :168-185), into the X slot of that round's parity; round r + 1 is assembled in the middle of round r
-      auto build_x = [&](long long bi0, int bnz, int rpar) {
+      const bool sparse_x = q.pat_n > 0 && q.pat_n * 3 < n * n;
+    auto build_x = [&](long long bi0, int bnz, int rpar) {
        for (int z = 0; z < bnz; ++z) {
         const long long item = bi0 + z;
         const long long b = item / q.T;
@@ -318,6 +319,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prog(const TcParams q, const
         __half* X = q.base[TC_CLS_SCR] + (size_t)(((long long)blockIdx.x * ILV + z) * TC_NSLOT + (rpar ? 4 : 0)) * mat;
         const int l16 = ld >> 4;
         const size_t nn = (size_t)n * n;
+        if (sparse_x) {
+          for (int e = et; e < q.pat_n; e += NEPI) scatter_x_entry(q, X, plane, ld, e, wts);
+        } else
         for (int i16 = et; i16 < n * l16; i16 += NEPI) {
           const int r = i16 / l16, c16 = (i16 - r * l16) * 16;
           float re[16], im[16];

@@ -55,6 +55,9 @@ struct TcParams {
   // EXPM
   int nops; const TcExpmOp* ops;
   int K, T; const double* ctrl; const double* maxA; const float2* A_f; float xscale;   // X' = xscale * (A_0 + sum u_k A_k)
+  // union sparsity pattern of A_0..A_K (sparse Hamiltonians: only these entries of X are ever written; the X slots / images
+  // are zero elsewhere): pat_rc[e] = row << 16 | column, pat_coef_f[e][K + 1]; pat_n = 0: dense assembly from A_f
+  int pat_n; const int* pat_rc; const float2* pat_coef_f;
   // SEG / CHAIN
   int L, S, chain_cls, chain_len;
   double2* Ufin; double* scal;

@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
     // generators of one round: X' = xscale (A_0 + sum_k u_k A_k), u_k = maxA_k sin(base[b][k][t]) (init_tf_ops_weight, :168-185);
     // every CTA of the cluster assembles a slice of 256 / CS rows and tells all of them
     const int xr0 = crank * (256 / CS), xr1 = min(n, xr0 + 256 / CS);
+    const bool sparse_x = q.pat_n > 0 && q.pat_n * 3 < n * n;
     auto build_x = [&](long long bi0, int bnz, int rpar) {
       for (int z = 0; z < bnz; ++z) {
         const long long item = bi0 + z;
@@ -310,6 +311,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
         __half* X = q.base[TC_CLS_SCR] + (size_t)((cid * ILV + z) * TC_NSLOT + (rpar ? 4 : 0)) * mat;
         const int l16 = ld >> 4;
         const size_t nn = (size_t)n * n;
+        if (sparse_x) {                              // entries dealt round-robin to the CTAs of the cluster
+          for (int e = crank * NEPI + et; e < q.pat_n; e += CS * NEPI) scatter_x_entry(q, X, plane, ld, e, wts);
+        } else
         for (int i16 = et; i16 < max(0, xr1 - xr0) * l16; i16 += NEPI) {
           const int rr = xr0 + i16 / l16, c16 = (i16 % l16) * 16;
           float re[16], im[16];

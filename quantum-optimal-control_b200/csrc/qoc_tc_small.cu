@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(448, 1) k_tc_small_expm(const TcParams q, cons
     long long tp[6] = {0, 0, 0, 0, 0, 0};            // cycles: X assembly, wait acc, tmem ld, math + stores, fences + arrive
     // generator X' = xscale (A_0 + sum_k u_k A_k), u_k = maxA_k sin(base[b][k][t]) (init_tf_ops_weight, tensorflow_state.py:168-185)
     // of the item this slot processes in round `rnd`, into the X image
+    const bool sparse_x = q.pat_n > 0 && q.pat_n * 3 < n * n;
     auto assemble_x = [&](int rnd) {
       const long long it = ((long long)rnd * gridDim.x + blockIdx.x) * NSL + s;
       const bool v = it < q.items;
@@ -228,7 +229,22 @@ __global__ void __launch_bounds__(448, 1) k_tc_small_expm(const TcParams q, cons
         if (et <= q.K) wts[s][et] = et == 0 ? q.xscale : (float)(q.maxA[et - 1] * sin(q.ctrl[((size_t)b * q.K + et - 1) * q.T + t])) * q.xscale;
       }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "r"(32 * QPS * WPQ) : "memory");
-      if (v && vrow) {
+      if (v && sparse_x) {
+        // sparse generators: one thread per entry of the union pattern (the rest of the X image is zero and stays zero)
+        for (int e = et; e < q.pat_n; e += 32 * QPS * WPQ) {
+          const int rc = __ldg(q.pat_rc + e), pr = rc >> 16, pc = rc & 0xffff;
+          const float2* cf = q.pat_coef_f + (size_t)e * (q.K + 1);
+          float xr = 0.f, xi = 0.f;
+          for (int k = 0; k <= q.K; ++k) { const float2 a = __ldg(cf + k); xr = fmaf(wts[s][k], a.x, xr); xi = fmaf(wts[s][k], a.y, xi); }
+          unsigned short r0, r1, i0, i1;
+          split1(xr, r0, r1); split1(xi, i0, i1);
+          const uint32_t o = imgX + img_off(pr, pc >> 3) + (uint32_t)((pc & 7) << 1);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(o), "h"(r0) : "memory");
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(o + pb), "h"(r1) : "memory");
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(o + 2 * pb), "h"(i0) : "memory");
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(o + 3 * pb), "h"(i1) : "memory");
+        }
+      } else if (v && vrow) {
         for (int c0 = 16 * cg; c0 < N16; c0 += 16 * WPQ) {
           float re[16], im[16];
 #pragma unroll
