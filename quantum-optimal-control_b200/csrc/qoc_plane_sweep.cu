@@ -13,6 +13,7 @@
 #include "qoc_internal.cuh"
 #include "qoc_tc_f16.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 #define DEVINL __device__ __forceinline__
 
@@ -342,6 +343,284 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep(QocParams p, const __ha
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// DMMA form of the sweeps.  A step is a GEMM with the states as N = 8 columns (m <= 8, zero-padded):
+//   forward : Psi(t+1)[row][j] = sum_k P[row][k] Psi(t)[k][j]          A = P rows of the chunk (fp16 pairs widened on the fly)
+//   reverse : Lam(t)[c][j]     = sum_r conj(P[r][c]) Lam(t+1)[r][j]    A = P^H, read transposed from the same row-major chunk
+// on mma.sync.m8n8k4.f64 with the 3M complex product (as qoc_mma_f64.cu).  The DFMA form above issues ~4 instructions per
+// useful FMA (shuffle reduce-scatter, vector re-reads per row, idle lanes when n/2 < 32); here a warp owns 8 x 8 output blocks.
+// K is permuted so that a lane's four consecutive k-steps read four consecutive columns of P (one 8-byte load per plane):
+// in the group of 16 k-values kk, DMMA step i of lane quarter-index q uses k = 16 kk + 4 q + i for A and B alike.
+// State vectors: vec[k][8] complex (k-major), slot of state j stored at j ^ (((k >> 2) & 3) << 1): the B-fragment loads
+// (lanes (q, g) read vec[16 kk + 4 q + i][g]) are then conflict-free.
+//   forward: the chunk has R rows = R/8 row blocks; with fewer row blocks than warps the k-groups are split over
+//            KS = NW / (R/8) warps per block and the partial blocks meet in shared memory;
+//   reverse: a warp owns column blocks (all of them stay in registers over the chunks of a step).
+// ------------------------------------------------------------------------------------------------------------------
+DEVINL void dmma884(double& d0, double& d1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+DEVINL int vslot(int k, int j) { return k * 8 + (j ^ (((k >> 2) & 3) << 1)); }
+
+struct MmaSweepShape { int nw, R, nst; size_t stage_halfs, smem; };
+
+MmaSweepShape mma_sweep_shape(int n, int B, int sms) {
+  MmaSweepShape s;
+  const int ld = tc_ld(n);
+  s.nw = n <= 64 ? 4 : n <= 128 ? 8 : 16;
+  const size_t stage_target = n <= 64 ? 10 * 1024 : n <= 128 ? 20 * 1024 : 58 * 1024;
+  int r = (int)(stage_target / (8 * (size_t)ld)) / 8 * 8;
+  if (r < 8) r = 8;
+  const int rfull = (n + 7) / 8 * 8;
+  s.R = r < rfull ? r : rfull;
+  s.stage_halfs = (size_t)4 * s.R * ld;
+  const size_t vec = (size_t)2 * ld * 8 * sizeof(cplx);
+  const size_t fixed = vec + (size_t)s.nw * 64 * sizeof(cplx) + 64 + 128;
+  size_t budget = n <= 64 ? 40 * 1024 : n <= 128 ? 100 * 1024 : 220 * 1024;
+  if (B > 0 && sms > 0) {
+    const int per_sm = (B + sms - 1) / sms;
+    if (per_sm >= 2 && per_sm <= 12) {
+      const size_t fit = (size_t)227 * 1024 / per_sm - 1024 - 256;
+      if (fit < budget && fit >= fixed + 2 * s.stage_halfs * sizeof(__half)) budget = fit;
+    }
+  }
+  int nst = budget > fixed ? (int)((budget - fixed) / (s.stage_halfs * sizeof(__half))) : 0;
+  if (nst > 8) nst = 8;
+  if (nst < 2 && fixed + 2 * s.stage_halfs * sizeof(__half) <= 220 * 1024) nst = 2;
+  s.nst = nst;
+  s.smem = fixed + (size_t)(nst > 0 ? nst : 0) * s.stage_halfs * sizeof(__half);
+  return s;
+}
+
+template <bool REV, int NW>
+__global__ void __launch_bounds__(32 * NW) k_plane_sweep_mma(QocParams p, const __half* __restrict__ Pp, int NST, int R) {
+  constexpr int NTH = 32 * NW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = p.n, m = p.m, T = p.T, mn = m * n;
+  const int ld = tc_ld(n);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int b = blockIdx.x;
+  const size_t stage_halfs = (size_t)4 * R * ld;
+  __half* ring = reinterpret_cast<__half*>(smem_raw);                                    // [NST][4][R][ld]
+  cplx* vecs = reinterpret_cast<cplx*>(smem_raw + (size_t)NST * stage_halfs * sizeof(__half));   // [2][ld][8]
+  cplx* part = vecs + (size_t)2 * ld * 8;                                                // [NW][64] partial blocks (forward)
+  uint64_t* full = reinterpret_cast<uint64_t*>(part + (size_t)NW * 64);                  // [NST]
+  const size_t plane = (size_t)n * ld, mat = 4 * plane;
+  const __half* Pb = Pp + (size_t)b * T * mat;
+  cplx* psi_b = p.psi + (size_t)b * (T + 1) * mn;
+  cplx* lam_b = p.lam + (size_t)b * (T + 1) * mn;
+  const int NC = (n + R - 1) / R;
+  const int nsteps = REV ? T - 1 : T;
+  const long long nchunks = (long long)nsteps * NC;
+  const double pscale = 1.0 / (double)(1 << TC_EU);
+  const int KG = ld >> 4;                                 // groups of 16 k-values
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto prefetch = [&](long long gi) {
+    if (gi < nchunks) {
+      const int step = (int)(gi / NC), c = (int)(gi - (long long)step * NC);
+      const int t = REV ? T - 1 - step : step;
+      const int rows = min(R, n - c * R);
+      uint64_t* bar = &full[gi % NST];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t bytes = (uint32_t)(rows * ld * sizeof(__half));
+      mbar_expect_tx(bar, 4 * bytes);
+      __half* dst = ring + (size_t)(gi % NST) * stage_halfs;
+      const __half* src = Pb + (size_t)t * mat + (size_t)c * R * ld;
+#pragma unroll
+      for (int pl = 0; pl < 4; ++pl) bulk_g2s(dst + (size_t)pl * R * ld, src + (size_t)pl * plane, bytes, bar);
+    }
+  };
+  const bool forb = REV && p.reg.has_forbidden && p.fw != nullptr;
+  const bool spd = REV && p.reg.has_speed_up != 0;
+  const double* sc = p.scal + (size_t)b * 8;
+  const double spdfac = REV ? sc[4] : 0.0;
+  auto source = [&](int t, int j, int r) -> cplx {         // regulariser sources (core/regularization_functions.py:71-95)
+    cplx s = make_double2(0.0, 0.0);
+    if (forb && p.dressW) {
+      s = p.psid[((size_t)b * (T + 1) + t) * mn + (size_t)j * n + r];
+    } else if (forb) {
+      const cplx x = psi_b[(size_t)t * mn + (size_t)j * n + r];
+      const double c = p.fw[r] / (double)T * 2.0 * (x.x * x.x + x.y * x.y);
+      s.x = c * x.x; s.y = c * x.y;
+    }
+    if (spd) {
+      const cplx qq = cmul(p.ot[(size_t)b * (T + 1) + t], p.phi[(size_t)j * n + r]);
+      s.x += spdfac * qq.x; s.y += spdfac * qq.y;
+    }
+    return s;
+  };
+
+  // stage rows beyond the matrix (last chunk) and the stage tails are read as A operands of rows / columns that are
+  // never stored: make them finite once
+  for (size_t e = tid; e < (size_t)NST * stage_halfs / 2; e += NTH) reinterpret_cast<uint32_t*>(ring)[e] = 0u;
+  for (int e = tid; e < 2 * ld * 8; e += NTH) vecs[e] = make_double2(0.0, 0.0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0)                                            // only now: the bulk copies must not race with the zero fill
+    for (int i = 0; i < NST - 1; ++i) prefetch(i);
+  for (int e = tid; e < m * n; e += NTH) {
+    const int j = e / n, r = e - j * n;
+    cplx v = make_double2(0.0, 0.0);
+    if (REV) {                                             // lambda(T) = -(2/m^2) o phi + source(T)
+      const double f = -2.0 / ((double)m * (double)m);
+      v = cmul(make_double2(sc[0] * f, sc[1] * f), p.phi[(size_t)j * n + r]);
+      const cplx s = source(T, j, r);
+      v.x += s.x; v.y += s.y;
+      lam_b[(size_t)T * mn + (size_t)j * n + r] = v;
+    } else {                                               // psi(0) = V is stored as is (:233-234); the chain starts from U0 V
+      for (int c = 0; c < n; ++c) {
+        const cplx u = p.U0[(size_t)r * n + c], a = p.V[(size_t)j * n + c];
+        v.x += u.x * a.x - u.y * a.y; v.y += u.x * a.y + u.y * a.x;
+      }
+      psi_b[(size_t)j * n + r] = p.V[(size_t)j * n + r];
+    }
+    vecs[vslot(r, j)] = v;
+  }
+
+  // four consecutive columns (k = c4 .. c4+3) of one row of the chunk: Re / Im as doubles (stored units)
+  auto load4 = [&](const __half* St, int rl, int c4, double (&ar)[4], double (&ai)[4]) {
+    const size_t ps = (size_t)R * ld;
+    const __half* pr = St + (size_t)rl * ld + c4;
+    const uint2 a0 = *reinterpret_cast<const uint2*>(pr), a1 = *reinterpret_cast<const uint2*>(pr + ps);
+    const uint2 b0 = *reinterpret_cast<const uint2*>(pr + 2 * ps), b1 = *reinterpret_cast<const uint2*>(pr + 3 * ps);
+    const double2 r01 = widen2(a0.x, a1.x), r23 = widen2(a0.y, a1.y), i01 = widen2(b0.x, b1.x), i23 = widen2(b0.y, b1.y);
+    ar[0] = r01.x; ar[1] = r01.y; ar[2] = r23.x; ar[3] = r23.y;
+    ai[0] = i01.x; ai[1] = i01.y; ai[2] = i23.x; ai[3] = i23.y;
+  };
+
+  int cur = 0;
+  long long gi = 0;
+  if (!REV) {
+    for (int step = 0; step < nsteps; ++step) {
+      const cplx* vc = vecs + (size_t)cur * ld * 8;
+      cplx* vn = vecs + (size_t)(cur ^ 1) * ld * 8;
+      for (int c = 0; c < NC; ++c, ++gi) {
+        __syncthreads();                                   // previous chunk's stage and partial blocks are free; c = 0: v(cur) complete
+        if (tid == 0) prefetch(gi + NST - 1);
+        while (!mbar_try_wait(&full[gi % NST], (uint32_t)(gi / NST) & 1u)) {}
+        const __half* St = ring + (size_t)(gi % NST) * stage_halfs;
+        const int rows = min(R, n - c * R);
+        const int nblk = (rows + 7) >> 3;
+        const int KS = max(1, NW / nblk);                  // warps per row block (k-groups dealt round-robin)
+        const int rb = warp % nblk, ksl = warp / nblk;
+        const bool active = ksl < KS;
+        double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0, t0 = 0.0, t1 = 0.0;
+        if (active) {
+          const int rl = min(rb * 8 + g, R - 1);
+          for (int kk = ksl; kk < KG; kk += KS) {
+            double ar[4], ai[4];
+            load4(St, rl, 16 * kk + 4 * q4, ar, ai);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k = 16 * kk + 4 * q4 + i;
+              const cplx bv = vc[vslot(k, g)];
+              dmma884(cr0, cr1, ar[i], bv.x);
+              dmma884(t0, t1, ai[i], bv.y);
+              dmma884(ci0, ci1, ar[i] + ai[i], bv.x + bv.y);
+            }
+          }
+        }
+        // C fragment: rows 8 rb + g, states 2 q4, 2 q4 + 1
+        cplx o0 = make_double2((cr0 - t0) * pscale, (ci0 - cr0 - t0) * pscale);
+        cplx o1 = make_double2((cr1 - t1) * pscale, (ci1 - cr1 - t1) * pscale);
+        if (KS > 1) {
+          if (active) { part[(size_t)warp * 64 + g * 8 + 2 * q4] = o0; part[(size_t)warp * 64 + g * 8 + 2 * q4 + 1] = o1; }
+          __syncthreads();
+          for (int e = tid; e < nblk * 64; e += NTH) {
+            const int bb = e >> 6, rr = (e >> 3) & 7, j = e & 7;
+            cplx v = make_double2(0.0, 0.0);
+            for (int s2 = 0; s2 < KS; ++s2) { const cplx x = part[(size_t)(s2 * nblk + bb) * 64 + rr * 8 + j]; v.x += x.x; v.y += x.y; }
+            const int row = c * R + bb * 8 + rr;
+            if (row < n) {
+              vn[vslot(row, j)] = v;
+              if (j < m) psi_b[(size_t)(step + 1) * mn + (size_t)j * n + row] = v;
+            }
+          }
+        } else if (active) {
+          const int row = c * R + rb * 8 + g;
+          if (row < n && rb * 8 + g < rows) {
+            const int j0 = 2 * q4;
+            vn[vslot(row, j0)] = o0; vn[vslot(row, j0 + 1)] = o1;
+            if (j0 < m) psi_b[(size_t)(step + 1) * mn + (size_t)j0 * n + row] = o0;
+            if (j0 + 1 < m) psi_b[(size_t)(step + 1) * mn + (size_t)(j0 + 1) * n + row] = o1;
+          }
+        }
+      }
+      cur ^= 1;
+    }
+  } else {
+    // a warp owns 16 columns (NW x 16 >= ld): lane g loads the two adjacent columns 16 w + 2 g, + 1 of its row with one 4-byte
+    // read per plane and feeds two "logical" 8-column blocks e = 0, 1 (block e = columns {16 w + 2 g + e}: a permutation of
+    // the output columns, resolved when the results are stored)
+    const int colb = 16 * warp + 2 * g;
+    const bool wact = 16 * warp < ld;
+    for (int step = 0; step < nsteps; ++step) {
+      const int t = T - 1 - step;
+      const cplx* vc = vecs + (size_t)cur * ld * 8;
+      cplx* vn = vecs + (size_t)(cur ^ 1) * ld * 8;
+      double cr[2][2], ci[2][2], t2[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) cr[u][0] = cr[u][1] = ci[u][0] = ci[u][1] = t2[u][0] = t2[u][1] = 0.0;
+      for (int c = 0; c < NC; ++c, ++gi) {
+        __syncthreads();                                   // previous chunk's stage is free (and, for c = 0, v(cur) complete)
+        if (tid == 0) prefetch(gi + NST - 1);
+        while (!mbar_try_wait(&full[gi % NST], (uint32_t)(gi / NST) & 1u)) {}
+        const __half* St = ring + (size_t)(gi % NST) * stage_halfs;
+        const size_t ps = (size_t)R * ld;
+        const int rows = min(R, n - c * R);
+        const int kq = (rows + 3) >> 2;                    // k-steps of this chunk: k = row of P = index of the state vector
+        if (wact) {
+          for (int ks = 0; ks < kq; ++ks) {
+            const int rl = 4 * ks + q4;                    // row inside the chunk
+            double2 ar = make_double2(0.0, 0.0), ai = make_double2(0.0, 0.0);
+            if (rl < rows) {
+              const __half* pr = St + (size_t)rl * ld + colb;
+              ar = widen2(*reinterpret_cast<const uint32_t*>(pr), *reinterpret_cast<const uint32_t*>(pr + ps));
+              ai = widen2(*reinterpret_cast<const uint32_t*>(pr + 2 * ps), *reinterpret_cast<const uint32_t*>(pr + 3 * ps));
+              ai.x = -ai.x; ai.y = -ai.y;                  // conj
+            }
+            const cplx bv = vc[vslot(min(c * R + rl, ld - 1), g)];
+            const double sb = bv.x + bv.y;
+            dmma884(cr[0][0], cr[0][1], ar.x, bv.x);
+            dmma884(t2[0][0], t2[0][1], ai.x, bv.y);
+            dmma884(ci[0][0], ci[0][1], ar.x + ai.x, sb);
+            dmma884(cr[1][0], cr[1][1], ar.y, bv.x);
+            dmma884(t2[1][0], t2[1][1], ai.y, bv.y);
+            dmma884(ci[1][0], ci[1][1], ar.y + ai.y, sb);
+          }
+        }
+      }
+      if (wact) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int col = colb + u;
+          if (col < n) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = 2 * q4 + e;
+              cplx v = make_double2((cr[u][e] - t2[u][e]) * pscale, (ci[u][e] - cr[u][e] - t2[u][e]) * pscale);
+              if (j < m) {
+                const cplx s = source(t, j, col);
+                v.x += s.x; v.y += s.y;
+                lam_b[(size_t)t * mn + (size_t)j * n + col] = v;
+              }
+              vn[vslot(col, j)] = v;
+            }
+          }
+        }
+      }
+      cur ^= 1;
+    }
+  }
+}
+
 }  // namespace
 
 bool qoc_plane_sweep_supported(int n, int m) {
@@ -365,11 +644,29 @@ static cudaError_t launch_ps(const QocParams& p, const void* planes, const Plane
   return launch_ps3<REV, MS, 16>(p, planes, s, st);
 }
 
+template <bool REV, int NW>
+static cudaError_t launch_psm(const QocParams& p, const void* planes, const MmaSweepShape& s, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_plane_sweep_mma<REV, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_plane_sweep_mma<REV, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  k_plane_sweep_mma<REV, NW><<<p.B, 32 * NW, s.smem, st>>>(p, reinterpret_cast<const __half*>(planes), s.nst, s.R);
+  return cudaGetLastError();
+}
+
 cudaError_t qoc_launch_plane_sweep(const QocParams& p, const void* planes, int reverse, cudaStream_t st, int64_t* launches) {
   if (!qoc_plane_sweep_supported(p.n, p.m)) return cudaErrorNotSupported;
   ++*launches;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  if (!(getenv("QOC_B200_SWEEP_MMA") && atoi(getenv("QOC_B200_SWEEP_MMA")) == 0)) {      // DMMA form (default); =0: the DFMA form
+    const MmaSweepShape ms = mma_sweep_shape(p.n, p.B, sms);
+    if (ms.nst >= 2) {
+      if (ms.nw == 4) return reverse ? launch_psm<true, 4>(p, planes, ms, st) : launch_psm<false, 4>(p, planes, ms, st);
+      if (ms.nw == 8) return reverse ? launch_psm<true, 8>(p, planes, ms, st) : launch_psm<false, 8>(p, planes, ms, st);
+      return reverse ? launch_psm<true, 16>(p, planes, ms, st) : launch_psm<false, 16>(p, planes, ms, st);
+    }
+  }
   const PlaneSweepShape s = plane_sweep_shape(p.n, p.m, p.B, sms);
   if (reverse) return launch_ps<true, 8>(p, planes, s, st);
   if (p.m <= 2) return launch_ps<false, 2>(p, planes, s, st);
