@@ -568,6 +568,15 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep_mma(QocParams p, const 
       double cr[2][2], ci[2][2], t2[2][2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) cr[u][0] = cr[u][1] = ci[u][0] = ci[u][1] = t2[u][0] = t2[u][1] = 0.0;
+      // the regulariser sources of this step (global reads of psi / psid) are requested now and consumed after the GEMM
+      cplx src[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = colb + u, j = 2 * q4 + e;
+          src[u][e] = (wact && col < n && j < m && (forb || spd)) ? source(t, j, col) : make_double2(0.0, 0.0);
+        }
       for (int c = 0; c < NC; ++c, ++gi) {
         __syncthreads();                                   // previous chunk's stage is free (and, for c = 0, v(cur) complete)
         if (tid == 0) prefetch(gi + NST - 1);
@@ -607,8 +616,7 @@ __global__ void __launch_bounds__(32 * NW) k_plane_sweep_mma(QocParams p, const 
               const int j = 2 * q4 + e;
               cplx v = make_double2((cr[u][e] - t2[u][e]) * pscale, (ci[u][e] - cr[u][e] - t2[u][e]) * pscale);
               if (j < m) {
-                const cplx s = source(t, j, col);
-                v.x += s.x; v.y += s.y;
+                v.x += src[u][e].x; v.y += src[u][e].y;
                 lam_b[(size_t)t * mn + (size_t)j * n + col] = v;
               }
               vn[vslot(col, j)] = v;
