@@ -58,7 +58,7 @@ def _complex_U(fs, n):
 # ------------------------------------------------------------------------------------------------------------------
 # fp32-class path against the reference's float32 AND float64 runs: n = 36, 64, 216
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ['c3_small_forbidden', 'c5_n64_m4', 'c4_T50'])
+@pytest.mark.parametrize("name", ['c3_small_forbidden', 'c5_n64_m4', 'c4_T50', 'c2_dressed_forbid', 'n5_U0', 'c2_small_allregs'])
 def test_f16x2_matches_reference_float32_goldens(name, built_lib):
     pb, conv, method, g64, g32 = _load_case(name)
     args, kw = W.grape_kwargs(pb)
