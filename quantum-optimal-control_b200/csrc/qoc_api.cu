@@ -532,6 +532,11 @@ static int tc_launch_xchain(qoc_handle_t h, const QocParams& p, cudaStream_t st)
   if (S >= 2) {
     q.prog = TC_PROG_SEG; q.items = (long long)p.B * S; q.T = p.T; q.L = L; q.S = S;
     ++h->launches;
+    const int pair_on = getenv("QOC_B200_TC_PAIR") ? atoi(getenv("QOC_B200_TC_PAIR")) : 1;
+    if (pair_on && tc_pair_supported(p.n) && p.T % L == 0 && tc_pair_max_clusters(2) > 0) {
+      q.ilv = QOC_TC_ILV; q.tma_store = 1;          // equal-length segments: the CTA-pair kernel, two segments interleaved
+      CUDA_TRY(h, tc_pair_launch_expm(q, h->tmaps, h->tsmaps, h->tg, 2, st));
+    } else
     CUDA_TRY(h, tc_launch(q, h->tmaps, h->tg, (int)(q.items < h->tc_grid ? q.items : h->tc_grid), st));
   }
   tc_base_params(h, q);

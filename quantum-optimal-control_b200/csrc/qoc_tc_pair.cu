@@ -90,11 +90,30 @@ DEVINL void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, i
 
 struct PairOp {
   long long a_idx, b_idx, e_idx, d1_idx, d2_idx;   // matrix indices; d?_cls < 0: none
-  int d1_cls, d2_cls;
+  int a_cls, b_cls, d1_cls, d2_cls;
   float c1[3], c2[3];
 };
 
+// products per item: EXPM = the op table; SEG = L - 1 products of a full segment (the launcher only sends problems with T % L == 0)
+DEVINL int pair_nops(const TcParams& q) { return q.prog == TC_PROG_SEG ? q.L - 1 : q.nops; }
+
 DEVINL void make_pair_op(const TcParams& q, long long item, int j, long long sb, int rpar, PairOp& o) {
+  o.a_cls = o.b_cls = TC_CLS_SCR;
+  if (q.prog == TC_PROG_SEG) {
+    // seg[b][sg] = P[b][t0 + L - 1] ... P[b][t0]  (re-associated chain, tensorflow_state.py:214-220): product j multiplies the
+    // running value (slots 2, 3) from the left by P[t0 + j + 1]
+    const long long bb = item / q.S;
+    const int sg = (int)(item % q.S);
+    const long long pb = bb * q.T + (long long)sg * q.L;
+    o.a_cls = TC_CLS_P; o.a_idx = pb + j + 1;
+    if (j == 0) { o.b_cls = TC_CLS_P; o.b_idx = pb; } else o.b_idx = sb + 2 + ((j - 1) & 1);
+    o.e_idx = 0;
+    o.d2_cls = -1; o.d2_idx = 0;
+    if (j == q.L - 2) { o.d1_cls = TC_CLS_SEG; o.d1_idx = item; } else { o.d1_cls = TC_CLS_SCR; o.d1_idx = sb + 2 + (j & 1); }
+    o.c1[0] = 1.0f / (float)(1 << TC_EU); o.c1[1] = o.c1[2] = 0.f;
+    o.c2[0] = o.c2[1] = o.c2[2] = 0.f;
+    return;
+  }
   const int xs = rpar ? 4 : 0;                    // the generator X of odd rounds lives in slot 4
   const TcExpmOp e = q.ops[j];
   o.a_idx = sb + (e.sa == 0 ? xs : e.sa);
@@ -132,6 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
   const size_t plane = (size_t)n * ld, mat = 4 * plane;
   long long t_wait0 = 0, t_wait1 = 0, t_work = 0;
   const int ILV = q.ilv;
+  const bool expm = q.prog == TC_PROG_EXPM;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
@@ -180,14 +200,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
       const uint32_t full0 = mapa(smem_u32(&bar_full[0]), (uint32_t)(crank & ~1));      // the leader's full barriers
       for (long long it0 = cid * ILV; it0 < q.items && ok; it0 += ncl * ILV, ++round) {
         const int nz = (int)min((long long)ILV, q.items - it0);
-        const int nops = q.nops;
+        const int nops = pair_nops(q);
         for (int j = 0; j < nops && ok; ++j)
           for (int z = 0; z < nz && ok; ++z) {
             PairOp o; make_pair_op(q, it0 + z, j, (cid * ILV + z) * TC_NSLOT, (int)(round & 1), o);
             const uint32_t tgt = base_ph + (j > 0 ? (uint32_t)((j - 1) * nz + z + 1) : 0u);
             const bool dep = j > 0;
             cat = j == 0 ? 0 : 1;
-            if (j == 0) need(4, (round + 1) * (uint32_t)CS);
+            if (expm && j == 0) need(4, (round + 1) * (uint32_t)CS);
             const int za = (int)o.a_idx, zb = (int)o.b_idx;
             for (int nh = nh_lo; nh < nh_hi && ok; ++nh) {
               const int nt = nh == 0 ? 128 : NT1;
@@ -205,8 +225,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
                 if (leader) mbar_expect_tx(&bar_full[s], 2 * STAGE_BYTES);
                 const uint32_t sa = smem_u32(smem) + s * STAGE_BYTES, sbb = sa + 4 * A_PLANE_BYTES;
                 const uint32_t fb = full0 + (uint32_t)(s * sizeof(uint64_t));
-                tma_load_4d_pair(sa, &maps.a[TC_CLS_SCR], kb * KB_ELEMS, r * 128, 0, za, fb);
-                tma_load_4d_pair(sbb, &maps.b[TC_CLS_SCR], col0, kb * KB_ELEMS, 0, zb, fb);
+                tma_load_4d_pair(sa, &maps.a[o.a_cls], kb * KB_ELEMS, r * 128, 0, za, fb);
+                tma_load_4d_pair(sbb, &maps.b[o.b_cls], col0, kb * KB_ELEMS, 0, zb, fb);
               }
             }
           }
@@ -229,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
       bool ok = true;
       for (long long it0 = cid * ILV; it0 < q.items && ok; it0 += ncl * ILV) {
         const int nz = (int)min((long long)ILV, q.items - it0);
-        const int nops = q.nops;
+        const int nops = pair_nops(q);
         for (int jz = 0; jz < nops * nz && ok; ++jz)
           for (int nh = nh_lo; nh < nh_hi && ok; ++nh, ++ti) {
             const int nt = nh == 0 ? 128 : NT1;
@@ -355,11 +375,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_pair_expm(const TcParams q, 
     };
     for (long long it0 = cid * ILV; it0 < q.items && ok; it0 += ncl * ILV, ++round) {
       const int nz = (int)min((long long)ILV, q.items - it0);
-      const int nops = q.nops;
-      if (round == 0) build_x(it0, nz, 0);
+      const int nops = pair_nops(q);
+      if (expm && round == 0) build_x(it0, nz, 0);
       for (int j = 0; j < nops && ok; ++j)
         for (int z = 0; z < nz && ok; ++z) {
-          if (z == 0 && j == (nops > 2 ? 2 : nops - 1)) {
+          if (expm && z == 0 && j == (nops > 2 ? 2 : nops - 1)) {
             const long long nx0 = it0 + ncl * ILV;
             if (nx0 < q.items) build_x(nx0, (int)min((long long)ILV, q.items - nx0), (int)((round + 1) & 1));
           }
@@ -504,7 +524,8 @@ int tc_pair_max_clusters(int cs) {
 
 // q: an EXPM program (tc_launch's fields); cs = CTAs per cluster (2 or 4); scratch must hold (clusters * ilv * TC_NSLOT) matrices
 cudaError_t tc_pair_launch_expm(const TcParams& q_in, const TcMaps& maps, const TcStoreMaps& smaps, const TcGeom& g, int cs, cudaStream_t st) {
-  if (!tc_pair_supported(g.n) || q_in.prog != TC_PROG_EXPM) return cudaErrorInvalidValue;
+  if (!tc_pair_supported(g.n) || (q_in.prog != TC_PROG_EXPM && q_in.prog != TC_PROG_SEG)) return cudaErrorInvalidValue;
+  if (q_in.prog == TC_PROG_SEG && (q_in.L < 2 || q_in.T % q_in.L != 0)) return cudaErrorInvalidValue;
   TcParams q = q_in;
   q.n = g.n; q.ld = g.ld; q.N16 = g.N16; q.KBLK = g.KBLK;
   if (q.ilv < 1) q.ilv = 1;

@@ -123,6 +123,8 @@ F16_CASES = {
         'dwdt': 0.1, 'forbidden_coeff_list': [2.0], 'states_forbidden_list': [7]}), 2),
     'c5_n128_m8': (lambda: W.c5_random(128, T=12), dict(states_concerned_list=list(range(8))), 2),
     'c5_n200_m5': (lambda: W.c5_random(200, T=6), dict(states_concerned_list=[0, 1, 64, 128, 199]), 1),
+    # T a multiple of the segment length: the U_final branch's segment products run on the CTA-pair kernel as well
+    'c5_n136_T32': (lambda: W.c5_random(136, T=32), dict(states_concerned_list=[0, 5, 135]), 2),
     'c5_n256_m2': (lambda: W.c5_random(256, T=4), dict(states_concerned_list=[3, 255]), 1),
     'n5_U0': (lambda: W.c5_random(5, T=15), dict(U0=np.linalg.qr(np.random.default_rng(5).normal(size=(5, 5)) +
                                                                   1j * np.random.default_rng(6).normal(size=(5, 5)))[0],
@@ -155,7 +157,7 @@ def test_f16x2_matches_fp64_oracle(name, built_lib):
     eng.close()
 
 
-@pytest.mark.parametrize("name,knob", [('c5_n200_m5', 'QOC_B200_TC_PAIR'), ('c5_n256_m2', 'QOC_B200_TC_PAIR'),
+@pytest.mark.parametrize("name,knob", [('c5_n200_m5', 'QOC_B200_TC_PAIR'), ('c5_n256_m2', 'QOC_B200_TC_PAIR'), ('c5_n136_T32', 'QOC_B200_TC_PAIR'),
                                        ('c3_T30', 'QOC_B200_TC_SMALL'), ('c5_n48_m3', 'QOC_B200_TC_SMALL'),
                                        ('c2_T40', 'QOC_B200_TC_SMALL')])
 def test_f16x2_engines_agree_bit_for_bit(name, knob, built_lib, monkeypatch):
@@ -172,11 +174,12 @@ def test_f16x2_engines_agree_bit_for_bit(name, knob, built_lib, monkeypatch):
         sp, eng = _engine(args, kw, guess, 'f16x2')
         base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
         out = eng.value_and_grad(base)
-        res[v] = (eng.propagators().clone(), out['loss'].clone(), out['grad'].clone())
+        res[v] = (eng.propagators().clone(), out['loss'].clone(), out['grad'].clone(), eng.evolve(base)['U_final'].clone())
         eng.poll_error()
         eng.close()
     assert torch.equal(res['1'][0], res['0'][0])
     assert torch.equal(res['1'][1], res['0'][1]) and torch.equal(res['1'][2], res['0'][2])
+    assert torch.equal(res['1'][3], res['0'][3])
 
 
 @pytest.mark.parametrize("name", ['c3_T30', 'c5_n48_m3'])
