@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
     if (l < len) {
       if (PF32) {
         const float* src = Pgf + (size_t)l * raw_floats;
-        float* stg = Pstage + (l & 1) * raw_floats;
+        float* stg = Pstage + (PFMT == 2 ? 0 : (l & 1)) * raw_floats;       // plane sets: ONE staging buffer (refilled right after its widening)
         for (int c = tid; c < raw_floats / 4; c += G) cp_async16(stg + 4 * c, src + 4 * c);
       } else {
         const cplx* src = Pg + (size_t)l * nn + tid;
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
     cp_async_commit();
   };
   auto widen = [&](int l, cplx* dst) {                     // PF32: raw tile of step l -> swizzled double2 operand
-    const float* stg = Pstage + (l & 1) * raw_floats;
+    const float* stg = Pstage + (PFMT == 2 ? 0 : (l & 1)) * raw_floats;
     const __half* sh = reinterpret_cast<const __half*>(stg);
     const int pl = n * ldh;
     const double sc = 1.0 / 8192.0;                        // 2^-TC_EU
@@ -769,19 +769,28 @@ __global__ void __launch_bounds__(MT<NP, RB, CB>::THREADS) k_segprod(QocParams p
     }
   };
   fetch(0, Xb);
-  fetch(1, Pb);
-  if (PF32) {
-    cp_async_wait<1>();
+  if (PFMT == 2) {
+    cp_async_wait<0>();
     __syncthreads();
     widen(0, Xb);
+    __syncthreads();                                       // the staging buffer is free again
+    fetch(1, nullptr);
+  } else {
+    fetch(1, Pb);
+    if (PF32) {
+      cp_async_wait<1>();
+      __syncthreads();
+      widen(0, Xb);
+    }
   }
   for (int l = 1; l < len; ++l) {
     if (PF32) {
       cp_async_wait<0>();
       __syncthreads();                                     // raw P_{t0+l} landed; X complete; Pb free (step l-1 done)
       widen(l, Pb);
-      fetch(l + 1, nullptr);                               // staging half (l+1)&1 == (l-1)&1 was consumed a step ago
-      __syncthreads();
+      if (PFMT == 2) __syncthreads();                      // single staging buffer: everybody has read it
+      fetch(l + 1, nullptr);                               // fp32 tiles: staging half (l+1)&1 == (l-1)&1 was consumed a step ago
+      if (PFMT != 2) __syncthreads();
     } else {
       fetch(l + 1, Pb + (l & 1) * T_::MAT);                // the buffer step l-1 used
       cp_async_wait<1>();
@@ -810,7 +819,7 @@ cudaError_t launch_segprod(const QocParams& p, int L, int S, cplx* seg_out, cuda
   typedef MT<NP, RB, CB> T_;
   constexpr int PF32 = PFMT;
   const size_t raw = PFMT == 2 ? (size_t)8 * p.n * ((p.n + 15) / 16 * 16) : (size_t)2048 * sizeof(float);
-  const size_t smem = PFMT ? (size_t)2 * T_::MAT * sizeof(cplx) + 2 * raw : (size_t)3 * T_::MAT * sizeof(cplx);
+  const size_t smem = PFMT == 2 ? (size_t)2 * T_::MAT * sizeof(cplx) + raw : PFMT ? (size_t)2 * T_::MAT * sizeof(cplx) + 2 * raw : (size_t)3 * T_::MAT * sizeof(cplx);
   cudaError_t e = cudaFuncSetAttribute(k_segprod<NP, RB, CB, PF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_segprod<NP, RB, CB, PF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
