@@ -36,9 +36,29 @@ elif os.environ.get("QOC_BENCH_PIN", "1") != "0" and hasattr(os, "sched_setaffin
         _cores = sorted(os.sched_getaffinity(0))
         _lw = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
         _lr = int(os.environ.get("LOCAL_RANK", "0")) % _lw
-        _per = len(_cores) // _lw
-        if _per >= 2:
-            os.sched_setaffinity(0, _cores[_lr * _per:(_lr + 1) * _per])
+        _mine = None
+        try:                                      # NUMA-aware: the cores next to this rank's GPU, shared out among the GPUs of that node
+            import pynvml
+            pynvml.nvmlInit()
+            _words = (max(_cores) + 64) // 64
+            _masks = []
+            _vis = [int(x) for x in os.environ["CUDA_VISIBLE_DEVICES"].split(",")] if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else list(range(_lw))
+            for _g in range(_lw):
+                _m = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(_vis[_g]), _words)
+                _masks.append(tuple(c for c in _cores if (_m[c // 64] >> (c % 64)) & 1))
+            _same = [g for g in range(_lw) if _masks[g] == _masks[_lr]]
+            _near = _masks[_lr]
+            if len(_near) // len(_same) >= 2:
+                _k, _p = _same.index(_lr), len(_near) // len(_same)
+                _mine = list(_near[_k * _p:(_k + 1) * _p])
+        except Exception:  # noqa: BLE001
+            _mine = None
+        if _mine is None:
+            _per = len(_cores) // _lw
+            if _per >= 2:
+                _mine = _cores[_lr * _per:(_lr + 1) * _per]
+        if _mine:
+            os.sched_setaffinity(0, _mine)
             os.environ.setdefault("OMP_WAIT_POLICY", "ACTIVE")
             os.environ.setdefault("OMP_PROC_BIND", "false")
     except OSError:
