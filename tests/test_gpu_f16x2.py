@@ -202,6 +202,47 @@ def test_f16x2_wide_products_match_narrow_ones(name, built_lib, monkeypatch):
     assert (res['1'][2] - res['0'][2]).abs().max().item() < 1e-5 * res['0'][2].abs().max().item()
 
 
+SHAPES = [  # (n, K, T, m, B): odd sizes, every engine boundary (32/33, 64/65, 128/129), T around the segment length, m = 1 .. 8
+    (3, 1, 7, 1, 2), (9, 2, 17, 3, 3), (31, 2, 16, 2, 2), (33, 3, 33, 7, 2), (47, 1, 48, 8, 2), (63, 2, 15, 5, 2), (65, 2, 32, 4, 2),
+    (97, 2, 18, 1, 2), (127, 3, 16, 6, 1), (129, 2, 32, 2, 2), (161, 1, 17, 8, 1), (209, 2, 16, 3, 1), (255, 2, 5, 2, 1),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "n%d_K%d_T%d_m%d" % s[:4])
+def test_f16x2_matches_f64_engine_on_odd_shapes(shape, built_lib):
+    """The fp32-class path against the fp64 path of the SAME library on shapes that sit on the engines' boundaries (tile
+    padding, partial chunks of the sweeps, segment remainders): propagators, states, loss, gradient, U_final."""
+    n, K, T, m, B = shape
+    pb = W.c5_random(n, T=T, K=K, seed=4000 + n)
+    rng = np.random.default_rng(n)
+    if n % 2 == 1 and n > 8:                      # sparse Hamiltonians (band + a few couplings): the pattern-scatter generator assembly
+        i, j = np.indices((n, n))
+        mask = (np.abs(i - j) <= 1) | ((i + 2 * j) % 11 == 0) | ((j + 2 * i) % 11 == 0)
+        pb['H0'] = pb['H0'] * mask * 3.0
+        pb['Hops'] = [h * mask * 3.0 for h in pb['Hops']]
+    pb['states_concerned_list'] = sorted(rng.choice(n, size=m, replace=False).tolist())
+    pb['reg_coeffs'] = {'dwdt': 0.05, 'forbidden_coeff_list': [1.5], 'states_forbidden_list': [n - 1]}
+    setups, guess, args, kw = make_case(pb, seed=17, B=B)
+    res = {}
+    for dt in ('f64', 'f16x2'):
+        sp, eng = _engine(args, kw, guess, dt)
+        base = torch.from_numpy(np.ascontiguousarray(sp.ops_weight_base)).cuda()
+        out = eng.value_and_grad(base)
+        ev = eng.evolve(base)
+        res[dt] = dict(loss=out['loss'].clone(), reg=out['reg_loss'].clone(), grad=out['grad'].clone(), U=ev['U_final'].clone(),
+                       iv=ev['inter_vecs'].clone(), us=out['unitary_scale'].clone())
+        eng.poll_error()
+        eng.close()
+    a, b = res['f64'], res['f16x2']
+    assert torch.isfinite(b['U']).all() and torch.isfinite(b['grad']).all()
+    assert (a['iv'] - b['iv']).abs().max().item() < 2e-6 + 3e-7 * T
+    assert (a['loss'] - b['loss']).abs().max().item() < 2e-6 + 2e-7 * T
+    assert (a['reg'] - b['reg']).abs().max().item() < (2e-6 + 2e-7 * T) * max(1.0, a['reg'].abs().max().item())
+    assert (a['grad'] - b['grad']).abs().max().item() < 1e-4 * a['grad'].abs().max().item()
+    assert (a['U'] - b['U']).flatten(1).norm(dim=1).max().item() < 1e-4 * np.sqrt(n * max(T, 10) / 10.0)
+    assert (a['us'] - b['us']).abs().max().item() < 2e-4
+
+
 def test_f16x2_rejects_what_it_does_not_cover(built_lib):
     from quantum_optimal_control.core.engine import GrapeEngine, QocError
     with pytest.raises(QocError):
